@@ -1,0 +1,178 @@
+/*
+ * b200vc.h -- C-ABI of the B200-native hot path for the KUIS-AI LHBDC / Flex-Rate B-frame codecs.
+ *
+ * The reference (KUIS-AI-Tekalp-Research-Group/video-compression) has NO FFI layer: its hot path is a
+ * chain of eager torch / CompressAI calls.  Each entry point below replaces one such chain; the comment
+ * above it cites the reference interface (file:line, relative to the reference root) it stands in for.
+ * The Python binding a maintainer adds on the reference side is the ctypes stub in INTEGRATION.md
+ * (shipped as video-compression_b200/b200vc/_lib.py).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless marked [host].
+ *   - tensors are fp32, NCHW, with H*W contiguous per channel plane (channel stride = H*W).  Where a
+ *     tensor may be a channel slice of a wider tensor the batch stride is passed explicitly (elements).
+ *   - the library never allocates, never synchronises and keeps no mutable global state; every call is
+ *     an asynchronous launch on `stream` (a cudaStream_t passed as void*), CUDA-graph capturable.
+ *   - return value: 0 on success, a negative B200VC_E* code otherwise; b200vc_last_error() returns a
+ *     thread-local message for the last failing call.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point returns B200VC_ECUDA.
+ */
+#ifndef B200VC_H_
+#define B200VC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200VC_VERSION 100
+
+#if defined(__GNUC__)
+#define B200VC_API __attribute__((visibility("default")))
+#else
+#define B200VC_API
+#endif
+
+enum {
+  B200VC_OK = 0,
+  B200VC_EINVAL = -1,   /* bad argument (null pointer, non-positive size, unsupported channel count) */
+  B200VC_ECUDA = -2,    /* CUDA runtime error at launch                                              */
+  B200VC_EUNSUPPORTED = -3
+};
+
+/* Warp geometry variants. */
+enum {
+  B200VC_WARP_LHBDC = 0, /* LHBDC/model/m.py:111-126, LHBDC/model/flow.py:15-25: pixel-centre linspace grid,
+                            flow/((W-1)/2), grid_sample(bilinear, border, align_corners=False)              */
+  B200VC_WARP_FLEX = 1,  /* Flex-Rate.../b_model/b_model.py:99-112: int grid + flow, 2*(x/W-0.5),
+                            grid_sample defaults (bilinear, zeros, align_corners=False)                      */
+  B200VC_WARP_AC1 = 2    /* ICIP2024/src/model/m.py:262-282, helpers.py:61-69, OJSP2025/video_model.py:668-676:
+                            linspace(-1,1) grid, grid_sample(bilinear, border, align_corners=True)           */
+};
+
+/* Arithmetic-form switches for the coordinate path (bit-parity experiments; default 0 = the form torch's
+ * CUDA kernels use: reciprocal-multiply for tensor/python-scalar division, FMA-contracted unnormalise). */
+enum {
+  B200VC_ARITH_NO_FMA = 1,   /* unnormalise as mul-then-sub (ATen CPU form is (g+1)*(W/2)-0.5) */
+  B200VC_ARITH_TRUE_DIV = 2  /* flow / ((W-1)/2) as an IEEE division (ATen CPU form)                           */
+};
+
+/* Blend modes. */
+enum {
+  B200VC_BLEND_MASK = 0,   /* LHBDC/model/m.py:63-67: pred = m*fw + (1-m)*bw ; res = x - pred (mask has 1 channel) */
+  B200VC_BLEND_NORMW = 1,  /* Flex-Rate.../b_model/b_model.py:68-73: mask = sigmoid(logits[2ch]); w=0.5*mask;
+                              pred = (w1*xb + w2*xa)/(w1+w2+1e-8) ; res = x - pred                                */
+  B200VC_BLEND_HALF = 2    /* ICIP2024/src/opt_helpers.py:35-36: pred = 0.5*w1 + (1-0.5)*w2                      */
+};
+
+B200VC_API int b200vc_version(void);
+B200VC_API const char* b200vc_last_error(void);
+/* Number of SMs of the current device. */
+B200VC_API int b200vc_sm_count(void);
+/* Number of CTAs (= number of fp64 partials) per sample the reducing entry points should be launched with
+ * for `elems_per_sample` elements.  A function of the size only, never of the device, so the partial-sum
+ * shapes -- and therefore the fp64 totals -- are identical on every GPU of a GOP-sharded run. */
+B200VC_API int b200vc_reduce_blocks(int64_t elems_per_sample);
+
+/* ---------------------------------------------------------------------------------------------- warp
+ * Replaces Model.backwarp / flow.backwarp / BidirFlowRef.backwarp / FlowGuidedB.warp (see enum above).
+ *   img  [N,C,H,W] (batch stride img_bs), flow [N,2,H,W] contiguous (ch0 = x, ch1 = y, pixels),
+ *   out  [N,C,H,W] (batch stride out_bs; lets the caller write straight into a concat buffer).
+ *   tab_x[W], tab_y[H]: the base grid exactly as the reference builds it with torch.linspace on the CPU
+ *   (LHBDC/model/m.py:113-116; ICIP2024/src/model/m.py:264-265); ignored (may be NULL) for WARP_FLEX.
+ */
+B200VC_API int b200vc_warp_f32(const float* img, int64_t img_bs, const float* flow, const float* tab_x,
+                    const float* tab_y, float* out, int64_t out_bs, int N, int C, int H, int W,
+                    int variant, int arith, void* stream);
+
+/* Fused LHBDC motion compensation: flow glue (LHBDC/model/m.py:55-59: chunk, + prior, crop, x4 bilinear
+ * upsample) + both backward warps (m.py:61) + channel concat (m.py:63, torch.cat([fw, bw])).
+ *   x_before, x_after [N,3,H,W] contiguous; flow_hat [N,4,h4,w4] (mv_compressor x_hat, padded quarter res);
+ *   flow_ab, flow_ba [N,2,h4,w4]; the crop [:hh,:ww] with 4*hh == H, 4*ww == W;
+ *   out [N,6,H,W] = cat(fw, bw); flows_out (nullable) [N,4,H,W] = cat(flow_cb_hat, flow_ca_hat).
+ */
+B200VC_API int b200vc_warp2_lhbdc_f32(const float* x_before, const float* x_after, const float* flow_hat,
+                           const float* flow_ab, const float* flow_ba, const float* tab_x,
+                           const float* tab_y, float* out, float* flows_out, int N, int H, int W, int h4,
+                           int w4, int arith, void* stream);
+
+/* ------------------------------------------------------------------------------------ blend / residual
+ * Replaces LHBDC/model/m.py:63-67, Flex-Rate.../b_model/b_model.py:68-73, ICIP2024/src/opt_helpers.py:35-45.
+ *   a, b: the two warped references [N,3,H,W] (batch strides a_bs, b_bs: may be halves of the concat
+ *   buffer); mask [N,1|2,H,W] (NULL for BLEND_HALF); x_cur [N,3,H,W]; pred, res (each nullable) [N,3,H,W].
+ *   sse_partials (nullable, double[N*n_blocks]) receives per-CTA sums of (clamp(pred,0,1) - x_cur)^2 -- the
+ *   search form only needs that scalar; reduce with b200vc_sum_partials_f64.  n_blocks = CTAs per sample.
+ */
+B200VC_API int b200vc_blend_residual_f32(int mode, const float* mask, const float* a, int64_t a_bs, const float* b,
+                              int64_t b_bs, const float* x_cur, float* pred, float* res,
+                              double* sse_partials, int n_blocks, int N, int H, int W, void* stream);
+
+/* ------------------------------------------------------------------------------------------ GDN / IGDN
+ * Replaces compressai.layers.GDN.forward (instantiated at LHBDC/model/layers.py:49-53,84-88,124-128,159-163).
+ * gdn_prepare applies CompressAI's NonNegativeParametrizer to the stored parameters once per weight
+ * version:  beta_eff = max(beta, beta_bound)^2 - pedestal ; gamma_eff = max(gamma, gamma_bound)^2 - pedestal.
+ * params_out layout (floats): [0,C) beta_eff | [C, C+C*C) gamma_eff row-major [i][j] | [.., +C*C) its transpose |
+ *   [.., +2*C*C) the tf32 hi / lo split of gamma_eff as 128B-swizzled K-major tcgen05 operand images.
+ * b200vc_gdn_params_floats(C) gives the size.
+ */
+B200VC_API int64_t b200vc_gdn_params_floats(int C);
+B200VC_API int b200vc_gdn_prepare_f32(const float* beta, const float* gamma, float beta_bound, float gamma_bound,
+                           float pedestal, float* params_out, int C, void* stream);
+/*   x, out [N,C,HW]; addend (nullable) [N,C,HW] is added to the result (the residual-block skip,
+ *   compressai ResidualBlockWithStride/ResidualBlockUpsample `out += identity`); out must not alias x or addend.
+ *   out_i = x_i * rsqrt(beta_i + sum_j gamma_ij x_j^2)    (inverse != 0: * sqrt).
+ *   impl: 0 = auto, 1 = CUDA-core fp32 kernel (any C % 32 == 0), 2 = tcgen05 3xTF32 kernel (C == 128).
+ */
+B200VC_API int b200vc_gdn_f32(const float* x, const float* params, const float* addend, float* out, int N, int C,
+                   int64_t HW, int inverse, int impl, void* stream);
+
+/* ----------------------------------------------------------------------- Gaussian conditional (Q1, Q2, Q4, Q5)
+ * Replaces GaussianConditional.forward / quantize("symbols") / build_indexes and the torch.log(lik).sum()
+ * bit sums (LHBDC/model/layers.py:102-103; LHBDC/model/m.py:73-91; Flex-Rate.../b_model/layers.py:145-146).
+ *   y [N,C,HW] contiguous; scales, means [N,C,HW] with batch stride sm_bs (they are the two channel chunks
+ *   of h_s's [N,2C,H,W] output: sm_bs = 2*C*HW);
+ *   inv_gain (nullable) [C]: y_hat is multiplied per channel on the way out (Flex inv_gain_unit, layers.py:146);
+ *   y_hat, lik (nullable) [N,C,HW]; symbols, indexes (nullable int32) [N,C,HW];
+ *   scale_table [n_table] (needed iff indexes != NULL);
+ *   bits_partials (nullable) double[N * blocks_per_sample]: per-CTA sums of -log2(lik); the grid is
+ *   blocks_per_sample x N (use b200vc_reduce_blocks(C*HW)).
+ */
+B200VC_API int b200vc_gauss_cond_f32(const float* y, const float* scales, const float* means, int64_t sm_bs,
+                          const float* inv_gain, float* y_hat, float* lik, int32_t* symbols,
+                          int32_t* indexes, const float* scale_table, int n_table, float scale_bound,
+                          float lik_bound, double* bits_partials, int blocks_per_sample, int N, int C,
+                          int64_t HW, void* stream);
+
+/* ------------------------------------------------------------------------ factorised prior (Q3, Q4, Q5)
+ * Replaces EntropyBottleneck.forward (eval) (LHBDC/model/layers.py:97-98 call sites).
+ * eb_prepare packs, per channel, softplus(_matrix{0..4}), _bias{0..4}, tanh(_factor{0..3}) and the median
+ * into 59 floats (layout in DESIGN.md); inputs are the raw CompressAI parameters, filters (3,3,3,3).
+ */
+#define B200VC_EB_PARAMS_PER_CHANNEL 59
+B200VC_API int b200vc_eb_prepare_f32(const float* const* matrices /*[host] 5 device ptrs*/,
+                          const float* const* biases /*[host] 5*/, const float* const* factors /*[host] 4*/,
+                          const float* quantiles /*[C,1,3]*/, float* packed /*[C,59]*/, int C, void* stream);
+/*   z [N,C,HW]; gain / inv_gain (nullable) [C] (Flex hyper_gain_unit / hyper_inv_gain_unit);
+ *   z_hat, lik (nullable) [N,C,HW]; symbols (nullable int32): round(z*gain - median);
+ *   bits_partials as above.
+ */
+B200VC_API int b200vc_entropy_bottleneck_f32(const float* z, const float* packed, const float* gain,
+                                  const float* inv_gain, float* z_hat, float* lik, int32_t* symbols,
+                                  float lik_bound, double* bits_partials, int blocks_per_sample, int N,
+                                  int C, int64_t HW, void* stream);
+
+/* out[s] = sum_{k < n_per} partials[s*n_per + k] in fixed order (deterministic: 1-GPU and N-GPU totals agree). */
+B200VC_API int b200vc_sum_partials_f64(const double* partials, int n_per, int n_out, double* out, void* stream);
+
+/* -------------------------------------------------------------------------------------------- metrics
+ * Replaces the D2H + numpy PSNR of LHBDC/test/testing.py:176-182: sum over the unpadded crop [:h,:w] of
+ * (round(clip(a)*255) - round(clip(b)*255))^2, as n_blocks per-CTA double partials (exact integers).
+ */
+B200VC_API int b200vc_sse_u8_f32(const float* a, const float* b, double* partials, int n_blocks, int N, int C,
+                      int H, int W, int h, int w, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200VC_H_ */

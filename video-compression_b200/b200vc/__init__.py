@@ -1,0 +1,18 @@
+"""b200vc -- B200 (sm_100a) native hot path for the KUIS-AI LHBDC / Flex-Rate hierarchical B-frame codecs:
+flow-driven bilinear backward warp, GDN/IGDN, quantise + Gaussian-conditional / factorised-prior likelihood.
+
+Layout
+  csrc/ (one level up)  hand-written CUDA kernels + the C-ABI of include/b200vc.h  -> libb200vc.so
+  _lib.py               ctypes binding (the only way into the kernels; no fallback)
+  ops.py                tensor-level wrappers (one per reference call chain)
+  modules.py            CompressAI-interface mirror (GDN, EntropyBottleneck, GaussianConditional, blocks)
+  lhbdc.py              LHBDC model mirror (Model, Network, MVCompressor, ResidualCompressor, Mask)
+  patch.py              patch(model): swap the kernels into a model built from the reference's own classes
+  gop.py / dist.py      hierarchical-GOP schedule, GOP sharding over ranks, record gathering
+  synthetic.py          seeded synthetic video + weight calibration (no datasets / checkpoints offline)
+"""
+from . import _lib, dist, gop, lhbdc, modules, ops, synthetic  # noqa: F401
+from .lhbdc import Model, encode_B_symbols  # noqa: F401
+from .patch import patch  # noqa: F401
+
+__version__ = "0.1.0"

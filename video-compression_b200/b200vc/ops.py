@@ -1,0 +1,317 @@
+"""Torch-tensor wrappers over the b200vc C-ABI (one function per reference call chain).
+
+Torch is plumbing here: it owns the device memory and the stream; all arithmetic happens in
+libb200vc.so.  Every wrapper validates device / dtype / layout in Python (the reference's error
+convention is Python exceptions) and raises ``RuntimeError`` on a non-zero return code.
+Non-CUDA inputs raise: there is no CPU fallback.
+"""
+import math
+
+import torch
+
+from . import _lib
+from ._lib import (ARITH_NO_FMA, ARITH_TRUE_DIV, BLEND_HALF, BLEND_MASK, BLEND_NORMW, WARP_AC1, WARP_FLEX,
+                   WARP_LHBDC)
+
+_VARIANTS = {"lhbdc": WARP_LHBDC, "flex": WARP_FLEX, "ac1": WARP_AC1}
+_BLENDS = {"mask": BLEND_MASK, "normw": BLEND_NORMW, "half": BLEND_HALF}
+_launches = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
+
+
+def launch_count():
+    return _launches
+
+
+def _count(n=1):
+    global _launches
+    _launches += n
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda_f32(t, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (b200vc has no CPU fallback), got device {t.device}")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name}: expected float32, got {t.dtype}")
+
+
+def _planes(t, name):
+    """Return (tensor, data_ptr, batch_stride) for an NCHW tensor whose (C,H,W) block is dense; a channel
+    slice of a wider tensor qualifies.  Anything else is made contiguous."""
+    _need_cuda_f32(t, name)
+    if t.dim() != 4:
+        raise RuntimeError(f"{name}: expected a 4-D NCHW tensor, got shape {tuple(t.shape)}")
+    N, C, H, W = t.shape
+    st = t.stride()
+    dense = st[3] == 1 and st[2] == W and st[1] == H * W and (N == 1 or st[0] >= C * H * W)
+    if not dense:
+        t = t.contiguous()
+        st = t.stride()
+    return t, t.data_ptr(), (st[0] if N > 1 else C * H * W)
+
+
+def _contig(t, name):
+    _need_cuda_f32(t, name)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ----------------------------------------------------------------------------------------- warp
+_tables = {}
+
+
+def grid_tables(variant, H, W, device):
+    """Base sampling grid, built exactly as the reference does (torch.linspace on the CPU), kept as two
+    1-D tables instead of a [1,2,H,W] tensor (LHBDC/model/m.py:113-118; ICIP2024/src/model/m.py:264-266)."""
+    key = (variant, H, W, str(device))
+    tab = _tables.get(key)
+    if tab is None:
+        if variant == "lhbdc":
+            tx = torch.linspace(-1.0 + (1.0 / W), 1.0 - (1.0 / W), W)
+            ty = torch.linspace(-1.0 + (1.0 / H), 1.0 - (1.0 / H), H)
+        elif variant == "ac1":
+            tx = torch.linspace(-1.0, 1.0, W)
+            ty = torch.linspace(-1.0, 1.0, H)
+        else:
+            raise ValueError(variant)
+        tab = (tx.to(device), ty.to(device))
+        _tables[key] = tab
+    return tab
+
+
+def backwarp(img, flow, variant="lhbdc", out=None, arith=0):
+    """Bilinear backward warp.  ``variant``: 'lhbdc' (Model.backwarp / flow.backwarp), 'flex'
+    (BidirFlowRef.backwarp) or 'ac1' (FlowGuidedB.warp / DMC.warp).  ``out`` may be a channel slice of a
+    concat buffer."""
+    if variant not in _VARIANTS:
+        raise ValueError(f"backwarp: unknown variant {variant!r}")
+    img, ip, ibs = _planes(img, "backwarp(img)")
+    flow = _contig(flow, "backwarp(flow)")
+    N, C, H, W = img.shape
+    if tuple(flow.shape) != (N, 2, H, W):
+        raise RuntimeError(f"backwarp: flow shape {tuple(flow.shape)} does not match image {tuple(img.shape)}")
+    if out is None:
+        out = torch.empty_like(img, memory_format=torch.contiguous_format)
+    o, op, obs = _planes(out, "backwarp(out)")
+    if o is not out or tuple(out.shape) != (N, C, H, W):
+        raise RuntimeError("backwarp: `out` must be a dense [N,C,H,W] block (channel slices are fine)")
+    if variant == "flex":
+        tx = ty = None
+    else:
+        tx, ty = grid_tables(variant, H, W, img.device)
+    lib = _lib.load()
+    rc = lib.b200vc_warp_f32(ip, ibs, flow.data_ptr(), tx.data_ptr() if tx is not None else None,
+                             ty.data_ptr() if ty is not None else None, op, obs, N, C, H, W, _VARIANTS[variant],
+                             arith, _stream())
+    _lib.check(rc, "warp_f32")
+    _count()
+    return out
+
+
+def warp2_lhbdc(x_before, x_after, flow_hat, flow_ab, flow_ba, return_flows=False, arith=0):
+    """Fused LHBDC/model/m.py:55-63: flow glue + two warps + concat -> [N,6,H,W] (and optionally the two
+    full-resolution flows [N,4,H,W])."""
+    xb = _contig(x_before, "warp2(x_before)")
+    xa = _contig(x_after, "warp2(x_after)")
+    fh = _contig(flow_hat, "warp2(flow_hat)")
+    fab = _contig(flow_ab, "warp2(flow_ab)")
+    fba = _contig(flow_ba, "warp2(flow_ba)")
+    N, C, H, W = xb.shape
+    if C != 3 or xa.shape != xb.shape:
+        raise RuntimeError("warp2_lhbdc: references must both be [N,3,H,W]")
+    h4, w4 = fh.shape[2], fh.shape[3]
+    if tuple(fh.shape) != (N, 4, h4, w4) or tuple(fab.shape) != (N, 2, h4, w4) or tuple(fba.shape) != (N, 2, h4, w4):
+        raise RuntimeError("warp2_lhbdc: flow_hat must be [N,4,h,w] and the priors [N,2,h,w]")
+    tx, ty = grid_tables("lhbdc", H, W, xb.device)
+    out = torch.empty((N, 6, H, W), device=xb.device, dtype=torch.float32)
+    flows = torch.empty((N, 4, H, W), device=xb.device, dtype=torch.float32) if return_flows else None
+    lib = _lib.load()
+    rc = lib.b200vc_warp2_lhbdc_f32(xb.data_ptr(), xa.data_ptr(), fh.data_ptr(), fab.data_ptr(), fba.data_ptr(),
+                                    tx.data_ptr(), ty.data_ptr(), out.data_ptr(),
+                                    flows.data_ptr() if flows is not None else None, N, H, W, h4, w4, arith,
+                                    _stream())
+    _lib.check(rc, "warp2_lhbdc_f32")
+    _count()
+    return (out, flows) if return_flows else out
+
+
+# ------------------------------------------------------------------------------- blend / residual
+def reduce_blocks(elems_per_sample):
+    return _lib.load().b200vc_reduce_blocks(int(elems_per_sample))
+
+
+def sum_partials(partials, n_per, n_out):
+    out = torch.empty(n_out, device=partials.device, dtype=torch.float64)
+    rc = _lib.load().b200vc_sum_partials_f64(partials.data_ptr(), n_per, n_out, out.data_ptr(), _stream())
+    _lib.check(rc, "sum_partials_f64")
+    _count()
+    return out
+
+
+def blend_residual(mode, mask, a, b, x_cur, want_pred=True, want_res=True, want_sse=False):
+    """mode 'mask' (LHBDC m.py:63-67), 'normw' (Flex b_model.py:68-73; mask = raw 2-ch logits) or 'half'
+    (ICIP2024 opt_helpers.py:35-45).  Returns (pred, res, sse[N] float64) with None for parts not requested."""
+    if mode not in _BLENDS:
+        raise ValueError(f"blend_residual: unknown mode {mode!r}")
+    a, ap, abs_ = _planes(a, "blend(a)")
+    b, bp, bbs = _planes(b, "blend(b)")
+    x = _contig(x_cur, "blend(x_cur)")
+    N, C, H, W = x.shape
+    if C != 3 or tuple(a.shape) != (N, 3, H, W) or tuple(b.shape) != (N, 3, H, W):
+        raise RuntimeError("blend_residual: a, b, x_cur must all be [N,3,H,W]")
+    mp = None
+    if mode != "half":
+        mask = _contig(mask, "blend(mask)")
+        want_c = 2 if mode == "normw" else 1
+        if tuple(mask.shape) != (N, want_c, H, W):
+            raise RuntimeError(f"blend_residual: mask must be [N,{want_c},H,W] for mode {mode!r}")
+        mp = mask.data_ptr()
+    pred = torch.empty_like(x) if want_pred else None
+    res = torch.empty_like(x) if want_res else None
+    nb = reduce_blocks(H * W)
+    part = torch.empty(N * nb, device=x.device, dtype=torch.float64) if want_sse else None
+    rc = _lib.load().b200vc_blend_residual_f32(
+        _BLENDS[mode], mp, ap, abs_, bp, bbs, x.data_ptr(), pred.data_ptr() if want_pred else None,
+        res.data_ptr() if want_res else None, part.data_ptr() if want_sse else None, nb, N, H, W, _stream())
+    _lib.check(rc, "blend_residual_f32")
+    _count()
+    sse = sum_partials(part, nb, N) if want_sse else None
+    return pred, res, sse
+
+
+def sse_u8(a, b, h, w):
+    """Sum over the crop [:h,:w] of (uint8(a) - uint8(b))^2 with float_to_uint8 = round(clip(x,0,1)*255)
+    (LHBDC/test/testing.py:176-182); returns a 1-element float64 device tensor (exact integer)."""
+    a = _contig(a, "sse_u8(a)")
+    b = _contig(b, "sse_u8(b)")
+    if a.shape != b.shape or a.dim() != 4:
+        raise RuntimeError("sse_u8: a and b must be NCHW tensors of the same shape")
+    N, C, H, W = a.shape
+    nb = reduce_blocks(N * C * h * w)
+    part = torch.empty(nb, device=a.device, dtype=torch.float64)
+    rc = _lib.load().b200vc_sse_u8_f32(a.data_ptr(), b.data_ptr(), part.data_ptr(), nb, N, C, H, W, h, w, _stream())
+    _lib.check(rc, "sse_u8_f32")
+    _count()
+    return sum_partials(part, nb, 1)
+
+
+# --------------------------------------------------------------------------------------- GDN
+def gdn_prepare(beta, gamma, beta_bound, gamma_bound, pedestal):
+    """NonNegativeParametrizer + operand images, once per weight version.  Returns the params tensor."""
+    _need_cuda_f32(beta, "gdn_prepare(beta)")
+    _need_cuda_f32(gamma, "gdn_prepare(gamma)")
+    C = beta.numel()
+    if tuple(gamma.shape) != (C, C):
+        raise RuntimeError(f"gdn_prepare: gamma must be [{C},{C}]")
+    lib = _lib.load()
+    params = torch.empty(lib.b200vc_gdn_params_floats(C), device=beta.device, dtype=torch.float32)
+    rc = lib.b200vc_gdn_prepare_f32(beta.detach().contiguous().data_ptr(), gamma.detach().contiguous().data_ptr(),
+                                    float(beta_bound), float(gamma_bound), float(pedestal), params.data_ptr(), C,
+                                    _stream())
+    _lib.check(rc, "gdn_prepare_f32")
+    _count()
+    return params
+
+
+def gdn(x, params, inverse=False, addend=None, impl=0):
+    """out = x * rsqrt(beta + gamma @ x^2) (IGDN: sqrt) [+ addend]; x is NCHW."""
+    x = _contig(x, "gdn(x)")
+    N, C, H, W = x.shape
+    if addend is not None:
+        addend = _contig(addend, "gdn(addend)")
+        if addend.shape != x.shape:
+            raise RuntimeError("gdn: addend shape mismatch")
+    out = torch.empty_like(x)
+    rc = _lib.load().b200vc_gdn_f32(x.data_ptr(), params.data_ptr(), addend.data_ptr() if addend is not None else None,
+                                    out.data_ptr(), N, C, H * W, 1 if inverse else 0, impl, _stream())
+    _lib.check(rc, "gdn_f32")
+    _count()
+    return out
+
+
+# ----------------------------------------------------------------------------- entropy models
+def gauss_cond(y, scales, means, scale_bound=0.11, lik_bound=1e-9, inv_gain=None, want_y_hat=True,
+               want_lik=True, want_bits=True, want_symbols=False, scale_table=None):
+    """GaussianConditional.forward (eval) [+ quantize('symbols') + build_indexes] + bit sums in one pass.
+    Returns dict(y_hat, lik, bits[N] float64 (= sum -log2 lik), symbols, indexes)."""
+    y = _contig(y, "gauss_cond(y)")
+    N, C, H, W = y.shape
+    scales, sp, sbs = _planes(scales, "gauss_cond(scales)")
+    means, mp, mbs = _planes(means, "gauss_cond(means)")
+    if tuple(scales.shape) != (N, C, H, W) or tuple(means.shape) != (N, C, H, W):
+        raise RuntimeError("gauss_cond: scales / means shape mismatch")
+    if sbs != mbs:
+        means = means.contiguous()
+        scales = scales.contiguous()
+        sp, mp, sbs = scales.data_ptr(), means.data_ptr(), C * H * W
+    dev = y.device
+    y_hat = torch.empty_like(y) if want_y_hat else None
+    lik = torch.empty_like(y) if want_lik else None
+    sym = torch.empty(y.shape, device=dev, dtype=torch.int32) if want_symbols else None
+    idx = torch.empty(y.shape, device=dev, dtype=torch.int32) if want_symbols else None
+    if want_symbols:
+        if scale_table is None or scale_table.numel() < 2:
+            raise RuntimeError("gauss_cond: symbols/indexes need the scale table (call update() first)")
+        scale_table = _contig(scale_table, "gauss_cond(scale_table)")
+    if inv_gain is not None:
+        inv_gain = _contig(inv_gain.reshape(-1), "gauss_cond(inv_gain)")
+        if inv_gain.numel() != C:
+            raise RuntimeError("gauss_cond: inv_gain must have C entries")
+    nb = reduce_blocks(C * H * W)
+    part = torch.empty(N * nb, device=dev, dtype=torch.float64) if want_bits else None
+    p = lambda t: t.data_ptr() if t is not None else None
+    rc = _lib.load().b200vc_gauss_cond_f32(
+        y.data_ptr(), sp, mp, sbs, p(inv_gain), p(y_hat), p(lik), p(sym), p(idx),
+        p(scale_table) if want_symbols else None, scale_table.numel() if want_symbols else 0, float(scale_bound),
+        float(lik_bound), p(part), nb, N, C, H * W, _stream())
+    _lib.check(rc, "gauss_cond_f32")
+    _count()
+    bits = sum_partials(part, nb, N) if want_bits else None
+    return {"y_hat": y_hat, "lik": lik, "bits": bits, "symbols": sym, "indexes": idx}
+
+
+def eb_prepare(matrices, biases, factors, quantiles):
+    """Pack softplus(_matrix*), _bias*, tanh(_factor*), median per channel -> [C,59]."""
+    import ctypes
+    C = quantiles.shape[0]
+    keep = [_contig(t.detach(), "eb_prepare") for t in list(matrices) + list(biases) + list(factors)]
+    q = _contig(quantiles.detach(), "eb_prepare(quantiles)")
+    arr = lambda ts: (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+    packed = torch.empty((C, _lib.EB_PARAMS_PER_CHANNEL), device=q.device, dtype=torch.float32)
+    rc = _lib.load().b200vc_eb_prepare_f32(arr(keep[0:5]), arr(keep[5:10]), arr(keep[10:14]), q.data_ptr(),
+                                           packed.data_ptr(), C, _stream())
+    _lib.check(rc, "eb_prepare_f32")
+    _count()
+    return packed
+
+
+def entropy_bottleneck(z, packed, lik_bound=1e-9, gain=None, inv_gain=None, want_z_hat=True, want_lik=True,
+                       want_bits=True, want_symbols=False):
+    """EntropyBottleneck.forward (eval) + bit sums.  Returns dict(z_hat, lik, bits[N], symbols)."""
+    z = _contig(z, "entropy_bottleneck(z)")
+    N, C, H, W = z.shape
+    if tuple(packed.shape) != (C, _lib.EB_PARAMS_PER_CHANNEL):
+        raise RuntimeError("entropy_bottleneck: packed parameter shape mismatch")
+    dev = z.device
+    z_hat = torch.empty_like(z) if want_z_hat else None
+    lik = torch.empty_like(z) if want_lik else None
+    sym = torch.empty(z.shape, device=dev, dtype=torch.int32) if want_symbols else None
+    for g, nm in ((gain, "gain"), (inv_gain, "inv_gain")):
+        if g is not None and g.numel() != C:
+            raise RuntimeError(f"entropy_bottleneck: {nm} must have C entries")
+    gain = _contig(gain.reshape(-1), "eb(gain)") if gain is not None else None
+    inv_gain = _contig(inv_gain.reshape(-1), "eb(inv_gain)") if inv_gain is not None else None
+    nb = reduce_blocks(C * H * W)
+    part = torch.empty(N * nb, device=dev, dtype=torch.float64) if want_bits else None
+    p = lambda t: t.data_ptr() if t is not None else None
+    rc = _lib.load().b200vc_entropy_bottleneck_f32(z.data_ptr(), packed.data_ptr(), p(gain), p(inv_gain), p(z_hat),
+                                                   p(lik), p(sym), float(lik_bound), p(part), nb, N, C, H * W,
+                                                   _stream())
+    _lib.check(rc, "entropy_bottleneck_f32")
+    _count()
+    bits = sum_partials(part, nb, N) if want_bits else None
+    return {"z_hat": z_hat, "lik": lik, "bits": bits, "symbols": sym}

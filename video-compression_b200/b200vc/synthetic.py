@@ -1,0 +1,78 @@
+"""Synthetic workloads (no datasets or checkpoints exist offline): the seeded video generator of
+SURVEY.md 8d config 2 and a deterministic re-scaling of random-init weights.
+
+Why re-scale: with torch's default initialisation the analysis transforms shrink activations ~5x, so every
+latent quantises to 0, every scale sits on the 0.11 clamp and SPyNet's flows are ~0.1 px -- the hot-path kernels
+would only ever see one branch.  ``calibrate_`` multiplies a handful of final-layer weights by fixed constants
+and perturbs GDN / factorised-prior parameters (seeded, CPU generator) so that flows reach a few pixels,
+latents span several integer bins and scales cover the 64-entry table.  It is pure tensor arithmetic on the
+state dict (no forward pass), so it applies identically to this package's ``lhbdc.Model`` and to any model
+with the reference's key layout.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+@torch.no_grad()
+def calibrate_(model, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    randn = lambda *s: torch.randn(*s, generator=g)
+    rand = lambda *s: torch.rand(*s, generator=g)
+
+    def put(p, value):
+        p.copy_(value.to(device=p.device, dtype=p.dtype))
+
+    for basic in model.FlowNet.netBasic:
+        last = basic.netBasic[8]
+        last.weight.mul_(3.0)
+        last.bias.mul_(3.0)
+    model.masknet.conv4.weight.mul_(60.0)
+    for comp in (model.mv_compressor, model.residual_compressor):
+        comp.g_a[6].weight.mul_(40.0)
+        comp.g_a[6].bias.mul_(40.0)
+        comp.h_a[8].weight.mul_(80.0)
+        comp.h_s[8].weight.mul_(40.0)
+        N = comp.h_s[8].weight.shape[0] // 2
+        put(comp.h_s[8].bias[:N], torch.exp(math.log(0.05) + rand(N) * (math.log(20.0) - math.log(0.05))))
+        for mod in comp.modules():
+            if type(mod).__name__ == "GDN":
+                C = mod.beta.numel()
+                ped = mod.beta_reparam.pedestal.cpu()
+                beta = 1.0 + 0.1 * randn(C).abs()
+                gamma = 0.1 * torch.eye(C) + 0.01 * randn(C, C).abs()
+                put(mod.beta, torch.sqrt(torch.max(beta + ped, ped)))
+                put(mod.gamma, torch.sqrt(torch.max(gamma + ped, ped)))
+        eb = comp.entropy_bottleneck
+        for i in range(5):
+            m = getattr(eb, f"_matrix{i}")
+            put(m, m.cpu() + 0.2 * randn(*m.shape))
+            if i < 4:
+                f = getattr(eb, f"_factor{i}")
+                put(f, 0.3 * randn(*f.shape))
+        q = eb.quantiles.cpu().clone()
+        q[:, 0, 1] = 0.5 * randn(q.shape[0])
+        put(eb.quantiles, q)
+    return model
+
+
+def make_sequence(T, H=1080, W=1920, seed=1234, device="cpu", max_motion=8, noise=0.01):
+    """[T,3,H,W] fp32 in [0,1]: a smooth random field (bicubic-upsampled uniform noise) seen through a window
+    that drifts by up to ``max_motion`` px per frame, plus ``noise`` white noise.
+    Generated on the CPU generator (same frames on every device), then moved."""
+    g = torch.Generator().manual_seed(seed)
+    margin = max_motion * 2 + 8
+    ch, cw = (H + 2 * margin + 31) // 32, (W + 2 * margin + 31) // 32
+    coarse = torch.rand(1, 3, ch + 1, cw + 1, generator=g)
+    canvas = F.interpolate(coarse, size=((ch + 1) * 32, (cw + 1) * 32), mode="bicubic", align_corners=False)
+    fine = torch.rand(1, 3, (ch + 1) * 4, (cw + 1) * 4, generator=g)
+    canvas = (0.8 * canvas + 0.2 * F.interpolate(fine, size=canvas.shape[-2:], mode="bilinear",
+                                                 align_corners=False)).clamp_(0, 1)[0]
+    frames = torch.empty(T, 3, H, W)
+    for t in range(T):
+        dx = margin + int(round(max_motion * math.sin(0.37 * t)))
+        dy = margin + int(round(0.5 * max_motion * math.cos(0.23 * t)))
+        win = canvas[:, dy:dy + H, dx:dx + W]
+        frames[t] = (win + noise * torch.randn(win.shape, generator=g)).clamp_(0, 1)
+    return frames.to(device)

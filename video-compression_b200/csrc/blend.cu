@@ -1,0 +1,188 @@
+// K-BLEND: mask blend + residual (+ optional SSE partials), and K-SSE: uint8-domain squared error.
+// Replaces LHBDC/model/m.py:63-67, Flex-Rate.../b_model/b_model.py:68-73, ICIP2024/src/opt_helpers.py:35-45
+// and the D2H + numpy PSNR of LHBDC/test/testing.py:176-182.
+//
+// Pure streaming (HBM-bound): 128-bit loads/stores, grid-stride over float4 units of one sample.
+// Each arithmetic step is rounded where torch's separate elementwise kernels round (no FMA contraction).
+#include "common.cuh"
+
+namespace b200vc {
+
+constexpr int kBlendThreads = 256;
+
+__device__ __forceinline__ float blend_one(int mode, float m0, float m1, float a, float b) {
+  if (mode == B200VC_BLEND_MASK) {
+    // mask*fw + (1.0 - mask)*bw
+    return __fadd_rn(__fmul_rn(m0, a), __fmul_rn(__fsub_rn(1.f, m0), b));
+  } else if (mode == B200VC_BLEND_NORMW) {
+    // w = 0.5*sigmoid(logit); (w1*xb + w2*xa)/(w1 + w2 + 1e-8)
+    const float w1 = __fmul_rn(0.5f, sigmoid_f(m0)), w2 = __fmul_rn(0.5f, sigmoid_f(m1));
+    const float num = __fadd_rn(__fmul_rn(w1, a), __fmul_rn(w2, b));
+    const float den = __fadd_rn(__fadd_rn(w1, w2), 1e-8f);
+    return __fdiv_rn(num, den);
+  }
+  // 0.5*w1 + (1-0.5)*w2
+  return __fadd_rn(__fmul_rn(0.5f, a), __fmul_rn(0.5f, b));
+}
+
+// One sample per blockIdx.y.  P = H*W (plane), planes4 = P/4 when VEC == 4.
+template <int VEC>
+__global__ void __launch_bounds__(kBlendThreads)
+blend_kernel(int mode, const float* __restrict__ mask, const float* __restrict__ a, int64_t a_bs,
+             const float* __restrict__ b, int64_t b_bs, const float* __restrict__ x,
+             float* __restrict__ pred, float* __restrict__ res, double* __restrict__ sse_partials, int64_t P) {
+  const int n = blockIdx.y;
+  const int mask_ch = (mode == B200VC_BLEND_NORMW) ? 2 : 1;
+  const float* mp = mask ? mask + (int64_t)n * mask_ch * P : nullptr;
+  const float* ap = a + (int64_t)n * a_bs;
+  const float* bp = b + (int64_t)n * b_bs;
+  const float* xp = x + (int64_t)n * 3 * P;
+  float* pp = pred ? pred + (int64_t)n * 3 * P : nullptr;
+  float* rp = res ? res + (int64_t)n * 3 * P : nullptr;
+  float sse = 0.f;
+  const int64_t units = P / VEC;
+  for (int64_t i = (int64_t)blockIdx.x * kBlendThreads + threadIdx.x; i < units;
+       i += (int64_t)gridDim.x * kBlendThreads) {
+    const int64_t o = i * VEC;
+    float m0[VEC], m1[VEC];
+    if constexpr (VEC == 4) {
+      float4 t = mp ? ld_stream4(mp + o) : make_float4(0, 0, 0, 0);
+      m0[0] = t.x; m0[1] = t.y; m0[2] = t.z; m0[3] = t.w;
+      if (mode == B200VC_BLEND_NORMW) t = ld_stream4(mp + P + o);
+      m1[0] = t.x; m1[1] = t.y; m1[2] = t.z; m1[3] = t.w;
+    } else {
+      m0[0] = mp ? mp[o] : 0.f;
+      m1[0] = (mode == B200VC_BLEND_NORMW) ? mp[P + o] : 0.f;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float av[VEC], bv[VEC], xv[VEC], pv[VEC], rv[VEC];
+      if constexpr (VEC == 4) {
+        const float4 ta = ld_stream4(ap + c * P + o), tb = ld_stream4(bp + c * P + o),
+                     tx = ld_stream4(xp + c * P + o);
+        av[0] = ta.x; av[1] = ta.y; av[2] = ta.z; av[3] = ta.w;
+        bv[0] = tb.x; bv[1] = tb.y; bv[2] = tb.z; bv[3] = tb.w;
+        xv[0] = tx.x; xv[1] = tx.y; xv[2] = tx.z; xv[3] = tx.w;
+      } else {
+        av[0] = ap[c * P + o]; bv[0] = bp[c * P + o]; xv[0] = xp[c * P + o];
+      }
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        pv[k] = blend_one(mode, m0[k], m1[k], av[k], bv[k]);
+        rv[k] = __fsub_rn(xv[k], pv[k]);
+        if (sse_partials) {
+          const float d = __fsub_rn(fminf(fmaxf(pv[k], 0.f), 1.f), xv[k]);
+          sse = __fmaf_rn(d, d, sse);
+        }
+      }
+      if constexpr (VEC == 4) {
+        if (pp) st_stream4(pp + c * P + o, make_float4(pv[0], pv[1], pv[2], pv[3]));
+        if (rp) st_stream4(rp + c * P + o, make_float4(rv[0], rv[1], rv[2], rv[3]));
+      } else {
+        if (pp) pp[c * P + o] = pv[0];
+        if (rp) rp[c * P + o] = rv[0];
+      }
+    }
+  }
+  if (sse_partials) {
+    const double tot = block_sum_to_f64<kBlendThreads>(sse);
+    if (threadIdx.x == 0) sse_partials[(int64_t)n * gridDim.x + blockIdx.x] = tot;
+  }
+}
+
+// uint8-domain SSE over the crop [:h,:w] of every plane: float_to_uint8 = round(clip(x,0,1)*255) (half-even).
+__global__ void __launch_bounds__(kBlendThreads)
+sse_u8_kernel(const float* __restrict__ a, const float* __restrict__ b, double* __restrict__ partials,
+              int planes, int H, int W, int h, int w) {
+  const int64_t total = (int64_t)planes * h * w;
+  float acc = 0.f;  // integer-valued; flushed to fp64 every 128 terms (128 * 255^2 < 2^24, so exact)
+  double dacc = 0.0;
+  int cnt = 0;
+  for (int64_t i = (int64_t)blockIdx.x * kBlendThreads + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * kBlendThreads) {
+    const int xx = (int)(i % w);
+    const int64_t r = i / w;
+    const int yy = (int)(r % h);
+    const int64_t pl = r / h;
+    const int64_t o = (pl * H + yy) * (int64_t)W + xx;
+    const float qa = rintf(__fmul_rn(fminf(fmaxf(__ldg(a + o), 0.f), 1.f), 255.f));
+    const float qb = rintf(__fmul_rn(fminf(fmaxf(__ldg(b + o), 0.f), 1.f), 255.f));
+    const float d = qa - qb;
+    acc += d * d;  // exact: integers, flushed to double before exceeding 2^24
+    if (++cnt == 128) {
+      dacc += (double)acc;
+      acc = 0.f;
+      cnt = 0;
+    }
+  }
+  dacc += (double)acc;
+  __shared__ double s_part[kBlendThreads / 32];
+  double d = warp_sum(dacc);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = d;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int i = 0; i < kBlendThreads / 32; ++i) tot += s_part[i];
+    partials[blockIdx.x] = tot;
+  }
+}
+
+__global__ void sum_partials_kernel(const double* __restrict__ partials, int n_per, double* __restrict__ out) {
+  // one CTA of 256 threads per output; fixed strided order then fixed tree => deterministic
+  const double* p = partials + (int64_t)blockIdx.x * n_per;
+  double v = 0.0;
+  for (int k = threadIdx.x; k < n_per; k += 256) v += p[k];
+  __shared__ double s_part[8];
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int i = 0; i < 8; ++i) tot += s_part[i];
+    out[blockIdx.x] = tot;
+  }
+}
+
+static bool aligned16(const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace b200vc
+
+using namespace b200vc;
+
+extern "C" int b200vc_blend_residual_f32(int mode, const float* mask, const float* a, int64_t a_bs,
+                                         const float* b, int64_t b_bs, const float* x_cur, float* pred,
+                                         float* res, double* sse_partials, int n_blocks, int N, int H, int W,
+                                         void* stream) {
+  B200VC_REQUIRE(a && b && x_cur, "blend_residual_f32: null pointer");
+  B200VC_REQUIRE(mode >= 0 && mode <= 2, "blend_residual_f32: unknown mode %d", mode);
+  B200VC_REQUIRE(mode == B200VC_BLEND_HALF || mask, "blend_residual_f32: mask required for mode %d", mode);
+  B200VC_REQUIRE(N > 0 && N <= 65535 && H > 0 && W > 0 && n_blocks > 0, "blend_residual_f32: bad shape");
+  const int64_t P = (int64_t)H * W;
+  const bool vec = (P % 4 == 0) && (a_bs % 4 == 0) && (b_bs % 4 == 0) && aligned16(mask) && aligned16(a) &&
+                   aligned16(b) && aligned16(x_cur) && aligned16(pred) && aligned16(res);
+  dim3 grid(n_blocks, N);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vec)
+    blend_kernel<4><<<grid, kBlendThreads, 0, st>>>(mode, mask, a, a_bs, b, b_bs, x_cur, pred, res,
+                                                    sse_partials, P);
+  else
+    blend_kernel<1><<<grid, kBlendThreads, 0, st>>>(mode, mask, a, a_bs, b, b_bs, x_cur, pred, res,
+                                                    sse_partials, P);
+  return check_launch("blend_residual_f32");
+}
+
+extern "C" int b200vc_sse_u8_f32(const float* a, const float* b, double* partials, int n_blocks, int N,
+                                 int C, int H, int W, int h, int w, void* stream) {
+  B200VC_REQUIRE(a && b && partials, "sse_u8_f32: null pointer");
+  B200VC_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && h > 0 && w > 0 && h <= H && w <= W && n_blocks > 0,
+                 "sse_u8_f32: bad shape");
+  sse_u8_kernel<<<n_blocks, kBlendThreads, 0, (cudaStream_t)stream>>>(a, b, partials, N * C, H, W, h, w);
+  return check_launch("sse_u8_f32");
+}
+
+extern "C" int b200vc_sum_partials_f64(const double* partials, int n_per, int n_out, double* out,
+                                       void* stream) {
+  B200VC_REQUIRE(partials && out && n_per > 0 && n_out > 0, "sum_partials_f64: bad argument");
+  sum_partials_kernel<<<n_out, 256, 0, (cudaStream_t)stream>>>(partials, n_per, out);
+  return check_launch("sum_partials_f64");
+}
