@@ -1,0 +1,94 @@
+"""GPU parity: K-GDN / K-IGDN through the C-ABI vs the oracle GDN (x**2 -> conv1x1 -> rsqrt/sqrt -> mul) run
+on the same device with TF32 disabled.  Tolerance 1e-5 relative (north star)."""
+import pytest
+import torch
+
+from oracle import cai
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(C, inverse, trained_like, seed=0):
+    from b200vc import modules
+    g = torch.Generator().manual_seed(seed)
+    o = cai.GDN(C, inverse=inverse)
+    if trained_like:  # gamma = 0.1*I + 0.01*|N|, beta = 1 + 0.1*|N|
+        with torch.no_grad():
+            ped = o.beta_reparam.pedestal
+            beta = 1.0 + 0.1 * torch.randn(C, generator=g).abs()
+            gamma = 0.1 * torch.eye(C) + 0.01 * torch.randn(C, C, generator=g).abs()
+            o.beta.copy_(torch.sqrt(torch.max(beta + ped, ped)))
+            o.gamma.copy_(torch.sqrt(torch.max(gamma + ped, ped)))
+    p = modules.GDN(C, inverse=inverse)
+    p.load_state_dict(o.state_dict())
+    return o.cuda().eval(), p.cuda().eval()
+
+
+def _x(N, C, H, W, seed=1):
+    g = torch.Generator().manual_seed(seed)
+    scale = torch.exp(torch.empty(1, C, 1, 1).uniform_(-2.3, 2.3, generator=g))  # logU[0.1, 10] per channel
+    return (torch.randn(N, C, H, W, generator=g) * scale).cuda()
+
+
+@pytest.mark.parametrize("impl", [1, 0])
+@pytest.mark.parametrize("inverse", [False, True])
+@pytest.mark.parametrize("C,shape", [(128, (1, 68, 120)), (128, (2, 33, 47)), (128, (1, 5, 8)), (64, (1, 40, 64)),
+                                     (192, (1, 34, 60)), (128, (1, 136, 240))])
+def test_gdn_matches_oracle(strict_fp32, impl, inverse, C, shape):
+    from b200vc import modules, ops
+    o, p = _pair(C, inverse, trained_like=True)
+    x = _x(shape[0], C, shape[1], shape[2])
+    with torch.no_grad():
+        want = o(x)
+        got = ops.gdn(x, modules.gdn_params(p), inverse=inverse, impl=impl)
+    err = ((got - want).abs() / want.abs().clamp(min=1e-6)).max().item()
+    print(f"gdn C={C} inv={inverse} impl={impl} {shape}: max rel err {err:.3e}")
+    assert err < 1e-5, err
+
+
+def test_gdn_at_init_closed_form_and_addend(strict_fp32):
+    from b200vc import modules
+    o, p = _pair(128, False, trained_like=False)
+    x = _x(1, 128, 20, 36)
+    skip = torch.randn_like(x)
+    with torch.no_grad():
+        got = modules.gdn_forward(p, x)
+        torch.testing.assert_close(got, x / torch.sqrt(1 + 0.1 * x ** 2), rtol=1e-5, atol=1e-7)
+        fused = modules.gdn_forward(p, x, addend=skip)
+        assert torch.equal(fused, got + skip)
+
+
+def test_gdn_params_track_weight_updates(strict_fp32):
+    from b200vc import modules
+    o, p = _pair(128, True, trained_like=True)
+    x = _x(1, 128, 8, 12)
+    with torch.no_grad():
+        a = p(x)
+        p.beta.mul_(1.5)
+        o.beta.mul_(1.5)
+        b = p(x)
+        assert not torch.equal(a, b)
+        torch.testing.assert_close(b, o(x), rtol=1e-5, atol=1e-7)
+
+
+def test_gdn_full_hd_layer_and_determinism(strict_fp32):
+    """Largest GDN of the 1080p residual path: [1,128,544,960]."""
+    from b200vc import modules
+    o, p = _pair(128, False, trained_like=True)
+    x = _x(1, 128, 544, 960)
+    with torch.no_grad():
+        want = o(x)
+        got = p(x)
+        again = p(x)
+    err = ((got - want).abs() / want.abs().clamp(min=1e-6)).max().item()
+    print(f"gdn 544x960: max rel err {err:.3e}")
+    assert err < 1e-5
+    assert torch.equal(got, again)
+
+
+def test_gdn_unsupported_channels_raise():
+    from b200vc import ops
+    x = torch.randn(1, 96, 4, 4, device="cuda")
+    params = torch.zeros(96 + 4 * 96 * 96, device="cuda")
+    with pytest.raises(RuntimeError, match="unsupported channel count"):
+        ops.gdn(x, params)

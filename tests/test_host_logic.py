@@ -1,0 +1,96 @@
+"""CPU: host-side logic of the product package -- interface mirror, checkpoint layout, GOP schedule and
+sharding, error behaviour (no CPU fallback)."""
+import pytest
+import torch
+
+import b200vc
+from b200vc import gop, modules, ops, synthetic
+from oracle import cai
+from oracle import lhbdc as o_lhbdc
+
+
+def test_checkpoint_layout_matches_the_reference_tree():
+    prod, orc = b200vc.Model(), o_lhbdc.Model()
+    a, b = prod.state_dict(), orc.state_dict()
+    assert list(a) and set(a) == set(b)
+    assert all(a[k].shape == b[k].shape and a[k].dtype == b[k].dtype for k in a)
+    prod.load_state_dict(b, strict=True)
+    # the CompressAI key names the reference's checkpoints carry
+    for k in ("mv_compressor.g_a.0.gdn.beta", "mv_compressor.g_a.0.gdn.gamma_reparam.lower_bound.bound",
+              "residual_compressor.g_s.1.igdn.gamma", "residual_compressor.entropy_bottleneck._matrix0",
+              "residual_compressor.entropy_bottleneck.quantiles", "mv_compressor.gaussian_conditional.scale_table",
+              "mv_compressor.gaussian_conditional.lower_bound_scale.bound", "FlowNet.netBasic.5.netBasic.8.weight",
+              "masknet.conv4.bias"):
+        assert k in a, k
+
+
+def test_module_mirror_has_the_compressai_surface():
+    for name in ("GDN", "EntropyBottleneck", "GaussianConditional", "ResidualBlock", "ResidualBlockUpsample",
+                 "ResidualBlockWithStride", "MeanScaleHyperprior", "conv3x3", "subpel_conv3x3"):
+        assert hasattr(modules, name) and hasattr(cai, name)
+    g, o = modules.GDN(16, inverse=True), cai.GDN(16, inverse=True)
+    assert torch.equal(g.beta, o.beta) and torch.equal(g.gamma, o.gamma) and g.inverse
+    e, oe = modules.EntropyBottleneck(8), cai.EntropyBottleneck(8)
+    assert torch.equal(e._matrix2, oe._matrix2) and torch.equal(e.quantiles, oe.quantiles)
+    assert torch.equal(e.target, oe.target)
+    m = b200vc.Model()
+    m.mv_compressor.update(force=True)
+    assert torch.equal(m.mv_compressor.gaussian_conditional.scale_table, cai.get_scale_table())
+
+
+def test_no_cpu_fallback():
+    x = torch.rand(1, 3, 8, 8)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        ops.backwarp(x, torch.zeros(1, 2, 8, 8))
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        modules.GDN(32).eval()(torch.rand(1, 32, 4, 4))
+    with pytest.raises(NotImplementedError):
+        modules.EntropyBottleneck(4).train()(torch.rand(1, 4, 2, 2))
+    with pytest.raises(NotImplementedError, match="next"):
+        b200vc.Model().mv_compressor.compress(torch.rand(1, 4, 64, 64))
+    with pytest.raises(ValueError):
+        ops.backwarp(x, x, variant="nope")
+
+
+def test_gop_schedules_match_the_reference_tables():
+    s = gop.LHBDC_GOP8
+    assert s.by_level() == [[4], [2, 6], [1, 3, 5, 7]]
+    # every frame's references are decoded before it (anchors 0 and gop are given)
+    for sch in (gop.LHBDC_GOP8, gop.FLEX_GOP16):
+        done = {0, sch.gop}
+        for f in sch.order:
+            a, b = sch.refs[f]
+            assert a in done and b in done and a < f < b and (f - a) == (b - f)
+            done.add(f)
+        assert done == set(range(sch.gop + 1))
+    assert gop.FLEX_GOP16.by_level()[0] == [8] and len(gop.FLEX_GOP16.by_level()) == 4
+    assert gop.num_gops(97, 8) == 12 and gop.num_gops(600, 8) == 74 and gop.num_gops(8, 8) == 0
+
+
+@pytest.mark.parametrize("units,world", [(74, 8), (12, 1), (38, 8), (3, 8), (0, 4)])
+def test_shard_units_is_a_contiguous_partition(units, world):
+    seen = []
+    for r in range(world):
+        rng = gop.shard_units(units, world, r)
+        seen += list(rng)
+        assert len(rng) in (units // world, units // world + 1)
+    assert seen == list(range(units))
+    with pytest.raises(ValueError):
+        gop.shard_units(4, 2, 2)
+
+
+def test_calibration_is_deterministic_and_layout_agnostic():
+    torch.manual_seed(0)
+    a = synthetic.calibrate_(o_lhbdc.Model(), 0).state_dict()
+    torch.manual_seed(0)
+    b = synthetic.calibrate_(o_lhbdc.Model(), 0).state_dict()
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    p = b200vc.Model()
+    p.load_state_dict(o_lhbdc.Model().state_dict())
+    synthetic.calibrate_(p, 3)  # same recipe applies to the product tree
+
+
+def test_psnr_from_sse():
+    sse = torch.tensor(3.0 * 10 * 10 * 4.0, dtype=torch.float64)  # every value off by 2
+    import math
+    assert abs(gop.psnr_from_sse(sse, 300).item() - 10 * math.log10(255.0 ** 2 / 4)) < 1e-9

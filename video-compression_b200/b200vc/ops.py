@@ -22,9 +22,41 @@ def launch_count():
     return _launches
 
 
-def _count(n=1):
+_prof = None  # name -> list of (start event, end event, algorithmic bytes) while profiling
+
+
+def profile_begin():
+    """Start recording a CUDA-event pair around every kernel launch made through this module (on the
+    launching stream).  bench.py uses it inside its timed region to get per-kernel durations live."""
+    global _prof
+    _prof = {}
+
+
+def profile_end():
+    """Stop recording; returns {kernel: {"launches", "ms", "bytes"}} (synchronises the device)."""
+    global _prof
+    rec, _prof = _prof or {}, None
+    torch.cuda.synchronize()
+    out = {}
+    for name, items in rec.items():
+        ms = sum(s.elapsed_time(e) for s, e, _ in items)
+        out[name] = {"launches": len(items), "ms": ms, "bytes": float(sum(b for _, _, b in items))}
+    return out
+
+
+def _run(name, nbytes, call):
+    """Launch one kernel through the C-ABI: count it, check the return code, optionally time it."""
     global _launches
-    _launches += n
+    _launches += 1
+    if _prof is None:
+        rc = call()
+    else:
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        rc = call()
+        e.record()
+        _prof.setdefault(name, []).append((s, e, nbytes))
+    _lib.check(rc, name)
 
 
 def _stream():
@@ -104,11 +136,9 @@ def backwarp(img, flow, variant="lhbdc", out=None, arith=0):
     else:
         tx, ty = grid_tables(variant, H, W, img.device)
     lib = _lib.load()
-    rc = lib.b200vc_warp_f32(ip, ibs, flow.data_ptr(), tx.data_ptr() if tx is not None else None,
-                             ty.data_ptr() if ty is not None else None, op, obs, N, C, H, W, _VARIANTS[variant],
-                             arith, _stream())
-    _lib.check(rc, "warp_f32")
-    _count()
+    _run("warp_f32", (2 * C + 2) * 4 * N * H * W, lambda: lib.b200vc_warp_f32(
+        ip, ibs, flow.data_ptr(), tx.data_ptr() if tx is not None else None,
+        ty.data_ptr() if ty is not None else None, op, obs, N, C, H, W, _VARIANTS[variant], arith, _stream()))
     return out
 
 
@@ -130,12 +160,11 @@ def warp2_lhbdc(x_before, x_after, flow_hat, flow_ab, flow_ba, return_flows=Fals
     out = torch.empty((N, 6, H, W), device=xb.device, dtype=torch.float32)
     flows = torch.empty((N, 4, H, W), device=xb.device, dtype=torch.float32) if return_flows else None
     lib = _lib.load()
-    rc = lib.b200vc_warp2_lhbdc_f32(xb.data_ptr(), xa.data_ptr(), fh.data_ptr(), fab.data_ptr(), fba.data_ptr(),
-                                    tx.data_ptr(), ty.data_ptr(), out.data_ptr(),
-                                    flows.data_ptr() if flows is not None else None, N, H, W, h4, w4, arith,
-                                    _stream())
-    _lib.check(rc, "warp2_lhbdc_f32")
-    _count()
+    # algorithmic bytes: 2 references in, 6-channel concat out, quarter-res flows (4+2+2 channels over HW/16)
+    nbytes = N * H * W * (12 * 4 + 8 * 4 / 16 + (16 if return_flows else 0))
+    _run("warp2_lhbdc_f32", nbytes, lambda: lib.b200vc_warp2_lhbdc_f32(
+        xb.data_ptr(), xa.data_ptr(), fh.data_ptr(), fab.data_ptr(), fba.data_ptr(), tx.data_ptr(), ty.data_ptr(),
+        out.data_ptr(), flows.data_ptr() if flows is not None else None, N, H, W, h4, w4, arith, _stream()))
     return (out, flows) if return_flows else out
 
 
@@ -146,9 +175,9 @@ def reduce_blocks(elems_per_sample):
 
 def sum_partials(partials, n_per, n_out):
     out = torch.empty(n_out, device=partials.device, dtype=torch.float64)
-    rc = _lib.load().b200vc_sum_partials_f64(partials.data_ptr(), n_per, n_out, out.data_ptr(), _stream())
-    _lib.check(rc, "sum_partials_f64")
-    _count()
+    lib = _lib.load()
+    _run("sum_partials_f64", 8 * (n_per + 1) * n_out, lambda: lib.b200vc_sum_partials_f64(
+        partials.data_ptr(), n_per, n_out, out.data_ptr(), _stream()))
     return out
 
 
@@ -174,11 +203,11 @@ def blend_residual(mode, mask, a, b, x_cur, want_pred=True, want_res=True, want_
     res = torch.empty_like(x) if want_res else None
     nb = reduce_blocks(H * W)
     part = torch.empty(N * nb, device=x.device, dtype=torch.float64) if want_sse else None
-    rc = _lib.load().b200vc_blend_residual_f32(
+    lib = _lib.load()
+    planes = 9 + (0 if mode == "half" else (2 if mode == "normw" else 1)) + 3 * int(want_pred) + 3 * int(want_res)
+    _run("blend_residual_f32", planes * 4 * N * H * W, lambda: lib.b200vc_blend_residual_f32(
         _BLENDS[mode], mp, ap, abs_, bp, bbs, x.data_ptr(), pred.data_ptr() if want_pred else None,
-        res.data_ptr() if want_res else None, part.data_ptr() if want_sse else None, nb, N, H, W, _stream())
-    _lib.check(rc, "blend_residual_f32")
-    _count()
+        res.data_ptr() if want_res else None, part.data_ptr() if want_sse else None, nb, N, H, W, _stream()))
     sse = sum_partials(part, nb, N) if want_sse else None
     return pred, res, sse
 
@@ -193,9 +222,9 @@ def sse_u8(a, b, h, w):
     N, C, H, W = a.shape
     nb = reduce_blocks(N * C * h * w)
     part = torch.empty(nb, device=a.device, dtype=torch.float64)
-    rc = _lib.load().b200vc_sse_u8_f32(a.data_ptr(), b.data_ptr(), part.data_ptr(), nb, N, C, H, W, h, w, _stream())
-    _lib.check(rc, "sse_u8_f32")
-    _count()
+    lib = _lib.load()
+    _run("sse_u8_f32", 8 * N * C * h * w, lambda: lib.b200vc_sse_u8_f32(
+        a.data_ptr(), b.data_ptr(), part.data_ptr(), nb, N, C, H, W, h, w, _stream()))
     return sum_partials(part, nb, 1)
 
 
@@ -209,11 +238,10 @@ def gdn_prepare(beta, gamma, beta_bound, gamma_bound, pedestal):
         raise RuntimeError(f"gdn_prepare: gamma must be [{C},{C}]")
     lib = _lib.load()
     params = torch.empty(lib.b200vc_gdn_params_floats(C), device=beta.device, dtype=torch.float32)
-    rc = lib.b200vc_gdn_prepare_f32(beta.detach().contiguous().data_ptr(), gamma.detach().contiguous().data_ptr(),
-                                    float(beta_bound), float(gamma_bound), float(pedestal), params.data_ptr(), C,
-                                    _stream())
-    _lib.check(rc, "gdn_prepare_f32")
-    _count()
+    b, g = beta.detach().contiguous(), gamma.detach().contiguous()
+    _run("gdn_prepare_f32", 4 * (C + 5 * C * C), lambda: lib.b200vc_gdn_prepare_f32(
+        b.data_ptr(), g.data_ptr(), float(beta_bound), float(gamma_bound), float(pedestal), params.data_ptr(), C,
+        _stream()))
     return params
 
 
@@ -226,10 +254,11 @@ def gdn(x, params, inverse=False, addend=None, impl=0):
         if addend.shape != x.shape:
             raise RuntimeError("gdn: addend shape mismatch")
     out = torch.empty_like(x)
-    rc = _lib.load().b200vc_gdn_f32(x.data_ptr(), params.data_ptr(), addend.data_ptr() if addend is not None else None,
-                                    out.data_ptr(), N, C, H * W, 1 if inverse else 0, impl, _stream())
-    _lib.check(rc, "gdn_f32")
-    _count()
+    lib = _lib.load()
+    nbytes = (2 + (addend is not None)) * C * 4 * N * H * W
+    _run("gdn_f32", nbytes, lambda: lib.b200vc_gdn_f32(
+        x.data_ptr(), params.data_ptr(), addend.data_ptr() if addend is not None else None, out.data_ptr(), N, C,
+        H * W, 1 if inverse else 0, impl, _stream()))
     return out
 
 
@@ -264,12 +293,12 @@ def gauss_cond(y, scales, means, scale_bound=0.11, lik_bound=1e-9, inv_gain=None
     nb = reduce_blocks(C * H * W)
     part = torch.empty(N * nb, device=dev, dtype=torch.float64) if want_bits else None
     p = lambda t: t.data_ptr() if t is not None else None
-    rc = _lib.load().b200vc_gauss_cond_f32(
+    lib = _lib.load()
+    words = 3 + int(want_y_hat) + int(want_lik) + 2 * int(want_symbols)
+    _run("gauss_cond_f32", words * 4 * y.numel(), lambda: lib.b200vc_gauss_cond_f32(
         y.data_ptr(), sp, mp, sbs, p(inv_gain), p(y_hat), p(lik), p(sym), p(idx),
         p(scale_table) if want_symbols else None, scale_table.numel() if want_symbols else 0, float(scale_bound),
-        float(lik_bound), p(part), nb, N, C, H * W, _stream())
-    _lib.check(rc, "gauss_cond_f32")
-    _count()
+        float(lik_bound), p(part), nb, N, C, H * W, _stream()))
     bits = sum_partials(part, nb, N) if want_bits else None
     return {"y_hat": y_hat, "lik": lik, "bits": bits, "symbols": sym, "indexes": idx}
 
@@ -282,10 +311,10 @@ def eb_prepare(matrices, biases, factors, quantiles):
     q = _contig(quantiles.detach(), "eb_prepare(quantiles)")
     arr = lambda ts: (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
     packed = torch.empty((C, _lib.EB_PARAMS_PER_CHANNEL), device=q.device, dtype=torch.float32)
-    rc = _lib.load().b200vc_eb_prepare_f32(arr(keep[0:5]), arr(keep[5:10]), arr(keep[10:14]), q.data_ptr(),
-                                           packed.data_ptr(), C, _stream())
-    _lib.check(rc, "eb_prepare_f32")
-    _count()
+    lib = _lib.load()
+    a_m, a_b, a_f = arr(keep[0:5]), arr(keep[5:10]), arr(keep[10:14])
+    _run("eb_prepare_f32", 4 * C * 2 * _lib.EB_PARAMS_PER_CHANNEL, lambda: lib.b200vc_eb_prepare_f32(
+        a_m, a_b, a_f, q.data_ptr(), packed.data_ptr(), C, _stream()))
     return packed
 
 
@@ -308,10 +337,10 @@ def entropy_bottleneck(z, packed, lik_bound=1e-9, gain=None, inv_gain=None, want
     nb = reduce_blocks(C * H * W)
     part = torch.empty(N * nb, device=dev, dtype=torch.float64) if want_bits else None
     p = lambda t: t.data_ptr() if t is not None else None
-    rc = _lib.load().b200vc_entropy_bottleneck_f32(z.data_ptr(), packed.data_ptr(), p(gain), p(inv_gain), p(z_hat),
-                                                   p(lik), p(sym), float(lik_bound), p(part), nb, N, C, H * W,
-                                                   _stream())
-    _lib.check(rc, "entropy_bottleneck_f32")
-    _count()
+    lib = _lib.load()
+    words = 1 + int(want_z_hat) + int(want_lik) + int(want_symbols)
+    _run("entropy_bottleneck_f32", words * 4 * z.numel(), lambda: lib.b200vc_entropy_bottleneck_f32(
+        z.data_ptr(), packed.data_ptr(), p(gain), p(inv_gain), p(z_hat), p(lik), p(sym), float(lik_bound), p(part),
+        nb, N, C, H * W, _stream()))
     bits = sum_partials(part, nb, N) if want_bits else None
     return {"z_hat": z_hat, "lik": lik, "bits": bits, "symbols": sym}
