@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--conv-tf32", action="store_true",
                     help="let cuDNN use TF32 for the (out-of-scope) convolutions, as torch defaults do")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ncu-range", action="store_true",
+                    help="bracket the timed region with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     ap.add_argument("--cpu-budget-s", type=float, default=240.0, help="wall-clock budget of the reference arm")
     return ap.parse_args()
 
@@ -257,12 +259,16 @@ def run_product(args):
     torch.cuda.synchronize()
     with ClockSampler(local_rank) as clocks:
         ops.profile_begin()
+        if args.ncu_range:
+            torch.cuda.profiler.start()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         for i in range(steps):
             bits, sse = step_resident(i)
         ev1.record()
         torch.cuda.synchronize()
+        if args.ncu_range:
+            torch.cuda.profiler.stop()
         prof = ops.profile_end()
         bd.barrier()
     ms_total = bd.max_over_ranks(ev0.elapsed_time(ev1), device)

@@ -334,7 +334,7 @@ def entropy_bottleneck(z, packed, lik_bound=1e-9, gain=None, inv_gain=None, want
             raise RuntimeError(f"entropy_bottleneck: {nm} must have C entries")
     gain = _contig(gain.reshape(-1), "eb(gain)") if gain is not None else None
     inv_gain = _contig(inv_gain.reshape(-1), "eb(inv_gain)") if inv_gain is not None else None
-    nb = reduce_blocks(C * H * W)
+    nb = reduce_blocks(4 * C * H * W)  # scalar kernel (heavy per-element math): one element per thread
     part = torch.empty(N * nb, device=dev, dtype=torch.float64) if want_bits else None
     p = lambda t: t.data_ptr() if t is not None else None
     lib = _lib.load()

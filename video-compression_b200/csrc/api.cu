@@ -57,9 +57,9 @@ int b200vc_sm_count(void) {
 
 int b200vc_reduce_blocks(int64_t elems_per_sample) {
   // Deterministic function of the size only (NOT of the device), so that partial-sum shapes -- and thus
-  // the fp64 totals -- are identical on every GPU of a sharded run.  Capped at 2 waves of 148 SMs x 4.
+  // the fp64 totals -- are identical on every GPU of a sharded run.  Capped at 148 SMs x 8 resident CTAs.
   if (elems_per_sample <= 0) return 1;
-  int64_t b = (elems_per_sample + 4095) / 4096;  // 256 threads x 4 floats x 4 iterations
+  int64_t b = (elems_per_sample + 1023) / 1024;  // 256 threads x one 128-bit access each
   if (b > 1184) b = 1184;
   if (b < 1) b = 1;
   return (int)b;
