@@ -113,7 +113,7 @@ B200VC_API int b200vc_blend_residual_f32(int mode, const float* mask, const floa
  * gdn_prepare applies CompressAI's NonNegativeParametrizer to the stored parameters once per weight
  * version:  beta_eff = max(beta, beta_bound)^2 - pedestal ; gamma_eff = max(gamma, gamma_bound)^2 - pedestal.
  * params_out layout (floats): [0,C) beta_eff | [C, C+C*C) gamma_eff row-major [i][j] | [.., +C*C) its transpose |
- *   [.., +2*C*C) the tf32 hi / lo split of gamma_eff as 128B-swizzled K-major tcgen05 operand images.
+ *   [.., +2*C*C) the tf32 hi / lo split of gamma_eff (row-major), the tensor-core kernel's A operand.
  * b200vc_gdn_params_floats(C) gives the size.
  */
 B200VC_API int64_t b200vc_gdn_params_floats(int C);

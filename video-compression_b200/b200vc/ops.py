@@ -6,6 +6,7 @@ convention is Python exceptions) and raises ``RuntimeError`` on a non-zero retur
 Non-CUDA inputs raise: there is no CPU fallback.
 """
 import math
+import os
 
 import torch
 
@@ -245,8 +246,15 @@ def gdn_prepare(beta, gamma, beta_bound, gamma_bound, pedestal):
     return params
 
 
+_GDN_IMPL = int(os.environ.get("B200VC_GDN_IMPL", "0"))  # 0 auto (tcgen05 when C == 128), 1 exact fp32, 2 tcgen05
+
+
 def gdn(x, params, inverse=False, addend=None, impl=0):
-    """out = x * rsqrt(beta + gamma @ x^2) (IGDN: sqrt) [+ addend]; x is NCHW."""
+    """out = x * rsqrt(beta + gamma @ x^2) (IGDN: sqrt) [+ addend]; x is NCHW.
+    impl 0 = auto: the tcgen05 3xTF32 kernel for C == 128 (~1e-6 relative), else the exact-fp32 CUDA-core
+    kernel; B200VC_GDN_IMPL=1 forces the exact kernel everywhere (bit-parity experiments)."""
+    if impl == 0:
+        impl = _GDN_IMPL
     x = _contig(x, "gdn(x)")
     N, C, H, W = x.shape
     if addend is not None:

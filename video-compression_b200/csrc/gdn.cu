@@ -17,18 +17,10 @@ namespace b200vc {
 int launch_gdn_tc(const float* x, const float* params, const float* addend, float* out, int N, int C, int64_t HW,
                   int inverse, cudaStream_t st);  // gdn_tc.cu
 
-// params: [0,C) beta | [C, C+C^2) gamma[i][j] | [C+C^2, C+2C^2) gammaT[j][i] | [C+2C^2, C+4C^2) tensor-core image
+// params: [0,C) beta | [C, C+C^2) gamma[i][j] | [C+C^2, C+2C^2) gammaT[j][i] | [C+2C^2, C+4C^2) tf32 hi[i][j], lo[i][j]
 __host__ __device__ inline int64_t gdn_off_gamma(int C) { return C; }
 __host__ __device__ inline int64_t gdn_off_gammaT(int C) { return (int64_t)C + (int64_t)C * C; }
 __host__ __device__ inline int64_t gdn_off_tc(int C) { return (int64_t)C + 2 * (int64_t)C * C; }
-
-// Element (row i, col k) of a K-major, 128-byte-swizzled tcgen05 operand tile set: the matrix is cut into
-// column blocks of 32 fp32 (=128 B); each block is [rows][32] with the 16-byte chunk index XOR-ed with (row & 7).
-__host__ __device__ inline int64_t tc_swizzled_index(int row, int col, int rows) {
-  const int kb = col >> 5, c = col & 31;
-  const int chunk = (c >> 2) ^ (row & 7);
-  return (int64_t)kb * rows * 32 + (int64_t)row * 32 + chunk * 4 + (c & 3);
-}
 
 __global__ void gdn_prepare_kernel(const float* __restrict__ beta, const float* __restrict__ gamma,
                                    float beta_bound, float gamma_bound, float pedestal,
@@ -50,9 +42,9 @@ __global__ void gdn_prepare_kernel(const float* __restrict__ beta, const float* 
     r &= 0xFFFFE000u;
     const float hi = __uint_as_float(r);
     const float lo = __fsub_rn(g, hi);
-    float* tc = params + gdn_off_tc(C);
-    tc[tc_swizzled_index(i, j, C)] = hi;
-    tc[(int64_t)C * C + tc_swizzled_index(i, j, C)] = lo;
+    float* tc = params + gdn_off_tc(C);  // row-major hi[i][j] then lo[i][j]: the tcgen05 kernel's TMEM image
+    tc[idx] = hi;
+    tc[(int64_t)C * C + idx] = lo;
   }
 }
 

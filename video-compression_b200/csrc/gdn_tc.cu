@@ -1,10 +1,400 @@
-// K-GDN on tcgen05 (3xTF32): placeholder until the tensor-core kernel lands; the dispatcher in gdn.cu falls
-// through to the CUDA-core fp32 kernel when this returns B200VC_EUNSUPPORTED.
+// K-GDN / K-IGDN on the 5th-gen tensor cores (tcgen05, sm_100a), C = 128.
+//
+//   norm[i, p] = beta_i + sum_j gamma[i, j] * x[j, p]^2       (the one dense contraction of the hot path)
+//   out[i, p]  = x[i, p] * (rsqrt | sqrt)(norm[i, p]) [+ addend[i, p]]
+//
+// fp32-class accuracy from TF32 tensor cores ("3xTF32"): x^2 = hi + lo and gamma = ghi + glo with hi/ghi rounded
+// to TF32 (cvt.rna) and lo/glo the exact remainders; D = ghi*hi + ghi*lo + glo*hi, fp32 accumulation in TMEM
+// (dropped term glo*lo ~ 2^-22 relative).  See DESIGN.md for the error budget.
+//
+// Mapping (one persistent CTA per SM, 320 threads, warp-specialised):
+//   * A operand  = gamma (M = 128 output channels x K = 128 input channels), resident in TMEM for the whole
+//     kernel (hi: columns [0,128), lo: [128,256)), written once with tcgen05.st.
+//   * B operand  = x^2 tile (K = 128 channels x N = 64 positions), MN-major (positions contiguous, exactly the
+//     NCHW layout), SWIZZLE_128B.  TMA loads the raw x tile as two [128 x 32] boxes whose 128B-swizzled image
+//     *is* the canonical MN-major UMMA layout, so the square/split pass is a pure elementwise smem->smem copy.
+//   * D          = 128 lanes (channels) x 64 columns (positions) fp32 in TMEM, double buffered.
+//   * warp 0: TMA producer | warp 1: TMEM alloc + MMA issuer (48 tcgen05.mma per tile) |
+//     warps 2-5: square + hi/lo split | warps 6-9: epilogue (tcgen05.ld -> +beta -> rsqrt/sqrt -> * x ->
+//     in-place into the raw tile -> TMA store).
+// Algorithmic HBM traffic: 2*128*4 B per position (+128*4 with addend); 3 * 2*128*128 tensor flop per position.
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace b200vc {
-int launch_gdn_tc(const float*, const float*, const float*, float*, int, int, int64_t, int, cudaStream_t) {
-  set_error("gdn_f32: tcgen05 kernel not built");
-  return B200VC_EUNSUPPORTED;
+
+namespace tc {
+
+constexpr int kC = 128;            // channels (UMMA M and K)
+constexpr int kTileP = 64;         // positions per tile (UMMA N)
+constexpr int kStages = 2;
+constexpr int kHalfBytes = kC * 32 * 4;          // one [128 x 32] fp32 box = 16 KB
+constexpr int kTileBytes = 2 * kHalfBytes;       // 32 KB
+constexpr int kStageBytes = 3 * kTileBytes;      // raw + hi + lo
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kThreads = 320;
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kColGhi = 0, kColGlo = 128, kColD = 256;
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  // bounded spin: a protocol bug must surface as a trap, never as a hung GPU
+  for (uint32_t spins = 0;; ++spins) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (spins > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_and_wait_read() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// SWIZZLE_128B, MN-major B operand: LBO = distance between the two 32-position atoms, SBO = distance between
+// groups of 8 channels (cute/atom/mma_traits_sm100.hpp make_umma_desc<Major::MN>).
+__device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((kHalfBytes >> 4) & 0x3FFF) << 16;  // leading byte offset  (16 KB)
+  d |= (uint64_t)((1024 >> 4) & 0x3FFF) << 32;        // stride byte offset   (8 rows x 128 B)
+  d |= (uint64_t)1 << 46;                              // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                              // SWIZZLE_128B
+  return d;
+}
+// kind::tf32, D = F32, A = B = TF32, A K-major (TMEM), B MN-major, N = 64, M = 128.
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (1u << 16) |
+                            ((uint32_t)(kTileP >> 3) << 17) | ((uint32_t)(kC >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(kIdesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,"
+      "%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
+      "%29,%30,%31,%32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+        "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+        "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+
+__device__ __forceinline__ float to_tf32_rna(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
+// params layout (gdn.cu): [0,C) beta | gamma | gammaT | hi[i][j] (C*C) | lo[i][j] (C*C)
+__global__ void __launch_bounds__(kThreads, 1)
+gdn_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_out,
+              const float* __restrict__ params, const float* __restrict__ addend, int64_t HW,
+              int tiles_per_sample, int total_tiles, int inverse) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  // per stage: raw | hi | lo
+  auto raw_addr = [&](int s) { return smem_base + s * kStageBytes; };
+  auto hi_addr = [&](int s) { return smem_base + s * kStageBytes + kTileBytes; };
+  auto lo_addr = [&](int s) { return smem_base + s * kStageBytes + 2 * kTileBytes; };
+  const uint32_t bar_base = smem_base + kStages * kStageBytes;
+  auto raw_full = [&](int s) { return bar_base + 8 * s; };
+  auto ab_full = [&](int s) { return bar_base + 16 + 8 * s; };
+  auto mma_done = [&](int s) { return bar_base + 32 + 8 * s; };
+  auto raw_empty = [&](int s) { return bar_base + 48 + 8 * s; };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + kStages * kStageBytes + 64);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(raw_full(s), 1);
+      mbar_init(ab_full(s), 128);
+      mbar_init(mma_done(s), 1);
+      mbar_init(raw_empty(s), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_out)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(const_cast<uint32_t*>(tmem_slot))), "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  // gamma hi/lo -> TMEM (lane = output channel i, column = input channel j), by the four epilogue warps
+  if (warp >= 6) {
+    const int q = warp & 3;
+    const int i = 32 * q + lane;
+    const float* hi = params + kC + 2 * kC * kC + (int64_t)i * kC;
+    const float* lo = hi + kC * kC;
+#pragma unroll 1
+    for (int part = 0; part < 8; ++part) {
+      const float* src = (part < 4 ? hi : lo) + (part & 3) * 32;
+      uint32_t v[32];
+#pragma unroll
+      for (int e = 0; e < 32; e += 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(src + e));
+        v[e] = __float_as_uint(t.x); v[e + 1] = __float_as_uint(t.y);
+        v[e + 2] = __float_as_uint(t.z); v[e + 3] = __float_as_uint(t.w);
+      }
+      tmem_st32(tmem + ((uint32_t)(32 * q) << 16) + (part < 4 ? kColGhi : kColGlo) + (part & 3) * 32, v);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int k = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++k) {
+        const int s = k & 1, ph = (k >> 1) & 1;
+        const int row0 = (tile / tiles_per_sample) * kC;
+        const int p0 = (tile % tiles_per_sample) * kTileP;
+        mbar_wait(raw_empty(s), ph ^ 1);
+        mbar_arrive_expect_tx(raw_full(s), kTileBytes);
+        tma_load_2d(raw_addr(s), &map_x, p0, row0, raw_full(s));
+        tma_load_2d(raw_addr(s) + kHalfBytes, &map_x, p0 + 32, row0, raw_full(s));
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      int k = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++k) {
+        const int s = k & 1, ph = (k >> 1) & 1;
+        mbar_wait(ab_full(s), ph);
+        tc_fence_after();
+        const uint32_t d = tmem + kColD + kTileP * s;
+#pragma unroll 1
+        for (int pass = 0; pass < 3; ++pass) {
+          // pass 0: ghi * hi   pass 1: ghi * lo   pass 2: glo * hi
+          const uint32_t a0 = tmem + (pass == 2 ? kColGlo : kColGhi);
+          const uint32_t b0 = (pass == 1) ? lo_addr(s) : hi_addr(s);
+#pragma unroll
+          for (int g = 0; g < kC / 8; ++g)
+            umma_tf32_ts(d, a0 + 8 * g, make_b_desc(b0 + g * 1024), (pass | g) != 0 ? 1u : 0u);
+        }
+        umma_commit(mma_done(s));
+      }
+    }
+  } else if (warp < 6) {
+    // ------------------------------------------------------------------ square + TF32 hi/lo split
+    const int t = threadIdx.x - 64;
+    int k = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++k) {
+      const int s = k & 1, ph = (k >> 1) & 1;
+      mbar_wait(raw_full(s), ph);
+      const float4* raw4 = reinterpret_cast<const float4*>(smem_gen + s * kStageBytes);
+      float4* hi4 = reinterpret_cast<float4*>(smem_gen + s * kStageBytes + kTileBytes);
+      float4* lo4 = reinterpret_cast<float4*>(smem_gen + s * kStageBytes + 2 * kTileBytes);
+#pragma unroll 4
+      for (int it = 0; it < kTileBytes / 16 / 128; ++it) {
+        const int idx = it * 128 + t;
+        const float4 v = raw4[idx];
+        float4 sq, h, l;
+        sq.x = __fmul_rn(v.x, v.x); sq.y = __fmul_rn(v.y, v.y); sq.z = __fmul_rn(v.z, v.z); sq.w = __fmul_rn(v.w, v.w);
+        h.x = to_tf32_rna(sq.x); h.y = to_tf32_rna(sq.y); h.z = to_tf32_rna(sq.z); h.w = to_tf32_rna(sq.w);
+        l.x = __fsub_rn(sq.x, h.x); l.y = __fsub_rn(sq.y, h.y); l.z = __fsub_rn(sq.z, h.z); l.w = __fsub_rn(sq.w, h.w);
+        hi4[idx] = h;
+        lo4[idx] = l;
+      }
+      fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+      mbar_arrive(ab_full(s));
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp & 3;
+    const int i = 32 * q + lane;  // output channel == TMEM lane
+    const float beta = __ldg(params + i);
+    const bool leader = (threadIdx.x == 6 * 32);
+    int k = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++k) {
+      const int s = k & 1, ph = (k >> 1) & 1;
+      const int n = tile / tiles_per_sample;
+      const int row0 = n * kC;
+      const int p0 = (tile % tiles_per_sample) * kTileP;
+      mbar_wait(mma_done(s), ph);
+      tc_fence_after();
+      float4* raw4 = reinterpret_cast<float4*>(smem_gen + s * kStageBytes);
+      const float* arow = addend ? addend + ((int64_t)row0 + i) * HW : nullptr;
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + kColD + kTileP * s + 32 * h, v);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float4* slot = raw4 + h * (kHalfBytes / 16) + i * 8 + (c ^ (i & 7));
+          const float4 x = *slot;
+          float nr[4], o[4];
+          const float xe[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            nr[e] = __fadd_rn(__uint_as_float(v[4 * c + e]), beta);
+            o[e] = __fmul_rn(xe[e], inverse ? sqrtf(nr[e]) : rsqrtf(nr[e]));
+          }
+          if (arow != nullptr) {
+            const int64_t p = (int64_t)p0 + 32 * h + 4 * c;
+            if (p < HW) {
+              const float4 a4 = *reinterpret_cast<const float4*>(arow + p);
+              o[0] = __fadd_rn(o[0], a4.x); o[1] = __fadd_rn(o[1], a4.y);
+              o[2] = __fadd_rn(o[2], a4.z); o[3] = __fadd_rn(o[3], a4.w);
+            }
+          }
+          *slot = make_float4(o[0], o[1], o[2], o[3]);
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();  // result tile (generic writes) -> visible to the TMA store
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (leader) {
+        tma_store_2d(&map_out, raw_addr(s), p0, row0);
+        if ((int64_t)p0 + 32 < HW) tma_store_2d(&map_out, raw_addr(s) + kHalfBytes, p0 + 32, row0);
+        tma_store_commit_and_wait_read();
+        mbar_arrive(raw_empty(s));
+      }
+    }
+    if (leader) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static bool make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t HW) {
+  EncodeTiledFn enc = encode_fn();
+  if (enc == nullptr) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)HW, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)HW * sizeof(float)};
+  cuuint32_t box[2] = {32, (cuuint32_t)kC};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+}  // namespace tc
+
+int launch_gdn_tc(const float* x, const float* params, const float* addend, float* out, int N, int C, int64_t HW,
+                  int inverse, cudaStream_t st) {
+  using namespace tc;
+  if (C != kC || HW % 4 != 0 || HW >= (1ll << 31) || (int64_t)N * C >= (1ll << 31)) {
+    set_error("gdn_f32: tcgen05 kernel needs C == 128 and HW %% 4 == 0 (got C=%d, HW=%lld)", C, (long long)HW);
+    return B200VC_EUNSUPPORTED;
+  }
+  CUtensorMap map_x, map_out;
+  if (!make_map(&map_x, x, (int64_t)N * C, HW) || !make_map(&map_out, out, (int64_t)N * C, HW)) {
+    set_error("gdn_f32: cuTensorMapEncodeTiled failed");
+    return B200VC_EUNSUPPORTED;
+  }
+  static bool configured[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !configured[dev]) {
+    if (cudaFuncSetAttribute(gdn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) {
+      set_error("gdn_f32: cannot reserve %d B of shared memory", kSmemBytes);
+      (void)cudaGetLastError();
+      return B200VC_EUNSUPPORTED;
+    }
+    configured[dev] = true;
+  }
+  const int64_t tps = (HW + kTileP - 1) / kTileP;
+  const int64_t total = tps * N;
+  if (total >= (1ll << 31)) {
+    set_error("gdn_f32: too many tiles");
+    return B200VC_EINVAL;
+  }
+  const int grid = (int)(total < sm_count() ? total : sm_count());
+  gdn_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(map_x, map_out, params, addend, HW, (int)tps, (int)total, inverse);
+  return check_launch("gdn_f32(tcgen05)");
+}
+
 }  // namespace b200vc

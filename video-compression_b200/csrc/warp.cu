@@ -6,10 +6,11 @@
 //   ICIP2024/src/model/m.py:262-282, OJSP2025/video_model.py:668-676 (WARP_AC1)
 // and, for warp2, LHBDC/model/m.py:55-63 (x4 flow upsample + both warps + concat).
 //
-// HBM-bound gather.  Layout NCHW planar fp32 (the reference layout).  One thread owns VEC=4 horizontally
-// adjacent output pixels: flow is read with one 128-bit load per plane, each output plane is written with
-// one 128-bit store, the four bilinear taps per pixel are scalar read-only loads that hit L1/L2 (neighbouring
-// threads sample neighbouring source pixels).  Algorithmic bytes: (2C+2)*4 per output pixel (C=3: 32 B/px).
+// HBM-bound gather.  Layout NCHW planar fp32 (the reference layout).  One thread owns one output pixel of a
+// 32 x 8 CTA tile: a warp's flow loads and plane stores are single fully-coalesced 128-byte transactions, and
+// its four bilinear taps per plane touch 1-2 L1 lines for smooth flows (a 4-pixel-per-thread layout was
+// measured 3x slower: 16-byte lane stride => 4-5 L1 wavefronts per gather, and 98-143 registers).
+// Algorithmic bytes: (2C+2)*4 per output pixel (C=3: 32 B/px); fused warp2: 50 B/px.
 //
 // The coordinate path reproduces ATen's CUDA arithmetic operation by operation:
 // every step is pinned with __f*_rn intrinsics so nvcc cannot re-associate or contract differently.
@@ -40,11 +41,18 @@ __device__ __forceinline__ float unnormalize(float g, int size, bool align_corne
   return c;
 }
 
+constexpr int kWarpThreads = 256;  // 32 (x) x 8 (y) output pixels per CTA, one pixel per thread
+
+// Border variants never need tap predicates: the clipped coordinate lies in [0, size-1], so only the "+1" tap
+// can leave the plane, and exactly then its weight is 0.  ATen skips that tap; we clamp its address and add
+// v * 0 (== skipping, for finite v).  The zeros variant (Flex) keeps ATen's per-tap bounds tests.
 struct Taps {
-  int off[4];   // plane offsets of nw, ne, sw, se (or -1 when out of bounds)
-  float w[4];
+  unsigned o00, o01, o10, o11;  // plane offsets of nw, ne, sw, se (32-bit: lets ptxas use [R.U32 + UR.64] addressing)
+  float w00, w01, w10, w11;
+  bool v00, v01, v10, v11;
 };
 
+template <bool BORDER>
 __device__ __forceinline__ Taps make_taps(float ix, float iy, int H, int W) {
   Taps t;
   const float fx = floorf(ix), fy = floorf(iy);
@@ -52,99 +60,110 @@ __device__ __forceinline__ Taps make_taps(float ix, float iy, int H, int W) {
   // ATen: nw = (ix_se - ix)*(iy_se - iy), ne = (ix - ix_sw)*(iy_sw - iy), sw = (ix_ne - ix)*(iy - iy_ne), se = ...
   const float dx1 = __fsub_rn((float)x1, ix), dx0 = __fsub_rn(ix, (float)x0);
   const float dy1 = __fsub_rn((float)y1, iy), dy0 = __fsub_rn(iy, (float)y0);
-  t.w[0] = __fmul_rn(dx1, dy1);
-  t.w[1] = __fmul_rn(dx0, dy1);
-  t.w[2] = __fmul_rn(dx1, dy0);
-  t.w[3] = __fmul_rn(dx0, dy0);
-  const bool vx0 = (x0 >= 0) & (x0 < W), vx1 = (x1 >= 0) & (x1 < W);
-  const bool vy0 = (y0 >= 0) & (y0 < H), vy1 = (y1 >= 0) & (y1 < H);
-  t.off[0] = (vx0 & vy0) ? y0 * W + x0 : -1;
-  t.off[1] = (vx1 & vy0) ? y0 * W + x1 : -1;
-  t.off[2] = (vx0 & vy1) ? y1 * W + x0 : -1;
-  t.off[3] = (vx1 & vy1) ? y1 * W + x1 : -1;
+  t.w00 = __fmul_rn(dx1, dy1);
+  t.w01 = __fmul_rn(dx0, dy1);
+  t.w10 = __fmul_rn(dx1, dy0);
+  t.w11 = __fmul_rn(dx0, dy0);
+  if (BORDER) {
+    const int x1c = min(x1, W - 1), y1c = min(y1, H - 1);
+    t.o00 = y0 * W + x0;
+    t.o01 = y0 * W + x1c;
+    t.o10 = y1c * W + x0;
+    t.o11 = y1c * W + x1c;
+    t.v00 = t.v01 = t.v10 = t.v11 = true;
+  } else {
+    const bool vx0 = (x0 >= 0) & (x0 < W), vx1 = (x1 >= 0) & (x1 < W);
+    const bool vy0 = (y0 >= 0) & (y0 < H), vy1 = (y1 >= 0) & (y1 < H);
+    t.v00 = vx0 & vy0; t.v01 = vx1 & vy0; t.v10 = vx0 & vy1; t.v11 = vx1 & vy1;
+    t.o00 = t.v00 ? y0 * W + x0 : 0;
+    t.o01 = t.v01 ? y0 * W + x1 : 0;
+    t.o10 = t.v10 ? y1 * W + x0 : 0;
+    t.o11 = t.v11 ? y1 * W + x1 : 0;
+  }
   return t;
 }
 
 // out_acc = 0; out_acc += v*w per in-bounds tap in nw, ne, sw, se order (nvcc contracts ATen's += into FMA).
+template <bool BORDER>
 __device__ __forceinline__ float sample(const float* __restrict__ plane, const Taps& t) {
+  if (BORDER) {
+    const float a = __ldg(plane + t.o00), b = __ldg(plane + t.o01), c = __ldg(plane + t.o10),
+                d = __ldg(plane + t.o11);
+    float acc = __fmaf_rn(a, t.w00, 0.f);
+    acc = __fmaf_rn(b, t.w01, acc);
+    acc = __fmaf_rn(c, t.w10, acc);
+    return __fmaf_rn(d, t.w11, acc);
+  }
   float acc = 0.f;
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-    if (t.off[k] >= 0) acc = __fmaf_rn(__ldg(plane + t.off[k]), t.w[k], acc);
+  if (t.v00) acc = __fmaf_rn(__ldg(plane + t.o00), t.w00, acc);
+  if (t.v01) acc = __fmaf_rn(__ldg(plane + t.o01), t.w01, acc);
+  if (t.v10) acc = __fmaf_rn(__ldg(plane + t.o10), t.w10, acc);
+  if (t.v11) acc = __fmaf_rn(__ldg(plane + t.o11), t.w11, acc);
   return acc;
 }
 
+// VARIANT and (for the production path) arith == 0 are compile-time so each instantiation carries one
+// straight-line coordinate chain.
+template <int VARIANT, bool ARITH0>
 __device__ __forceinline__ void coords(const WarpGeom& g, int x, int y, float u, float v, float tx, float ty,
                                        float& ix, float& iy) {
   float gx, gy;
-  if (g.variant == B200VC_WARP_FLEX) {
+  const int arith = ARITH0 ? 0 : g.arith;
+  if (VARIANT == B200VC_WARP_FLEX) {
     // x = gridX.float() + u ; normx = 2*(x/W - 0.5)          (b_model.py:106-109)
     const float xs = __fadd_rn((float)x, u), ys = __fadd_rn((float)y, v);
-    const float qx = (g.arith & B200VC_ARITH_TRUE_DIV) ? __fdiv_rn(xs, g.den_x) : __fmul_rn(xs, g.inv_x);
-    const float qy = (g.arith & B200VC_ARITH_TRUE_DIV) ? __fdiv_rn(ys, g.den_y) : __fmul_rn(ys, g.inv_y);
+    const float qx = (arith & B200VC_ARITH_TRUE_DIV) ? __fdiv_rn(xs, g.den_x) : __fmul_rn(xs, g.inv_x);
+    const float qy = (arith & B200VC_ARITH_TRUE_DIV) ? __fdiv_rn(ys, g.den_y) : __fmul_rn(ys, g.inv_y);
     gx = __fmul_rn(2.f, __fsub_rn(qx, 0.5f));
     gy = __fmul_rn(2.f, __fsub_rn(qy, 0.5f));
-    ix = unnormalize(gx, g.W, false, false, g.arith);
-    iy = unnormalize(gy, g.H, false, false, g.arith);
+    ix = unnormalize(gx, g.W, false, false, arith);
+    iy = unnormalize(gy, g.H, false, false, arith);
   } else {
     // grid + flow / ((W-1)/2)                                  (m.py:121-125)
-    const float nu = (g.arith & B200VC_ARITH_TRUE_DIV) ? __fdiv_rn(u, g.den_x) : __fmul_rn(u, g.inv_x);
-    const float nv = (g.arith & B200VC_ARITH_TRUE_DIV) ? __fdiv_rn(v, g.den_y) : __fmul_rn(v, g.inv_y);
+    const float nu = (arith & B200VC_ARITH_TRUE_DIV) ? __fdiv_rn(u, g.den_x) : __fmul_rn(u, g.inv_x);
+    const float nv = (arith & B200VC_ARITH_TRUE_DIV) ? __fdiv_rn(v, g.den_y) : __fmul_rn(v, g.inv_y);
     gx = __fadd_rn(tx, nu);
     gy = __fadd_rn(ty, nv);
-    const bool ac = (g.variant == B200VC_WARP_AC1);
-    ix = unnormalize(gx, g.W, ac, true, g.arith);
-    iy = unnormalize(gy, g.H, ac, true, g.arith);
+    constexpr bool ac = (VARIANT == B200VC_WARP_AC1);
+    ix = unnormalize(gx, g.W, ac, true, arith);
+    iy = unnormalize(gy, g.H, ac, true, arith);
   }
 }
 
-constexpr int kWarpThreads = 256;
-
-template <int VEC>
+// CT > 0: channel count known at compile time (planes unrolled, all gathers of a pixel in flight together).
+template <int CT, int VARIANT, bool ARITH0>
 __global__ void __launch_bounds__(kWarpThreads)
 warp_kernel(const float* __restrict__ img, int64_t img_bs, const float* __restrict__ flow,
             const float* __restrict__ tab_x, const float* __restrict__ tab_y, float* __restrict__ out,
             int64_t out_bs, int C, WarpGeom g) {
-  const int Wv = (g.W + VEC - 1) / VEC;
-  const int xv = blockIdx.x * 32 + (threadIdx.x & 31);
+  constexpr bool BORDER = (VARIANT != B200VC_WARP_FLEX);
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
   const int y = blockIdx.y * (kWarpThreads / 32) + (threadIdx.x >> 5);
   const int n = blockIdx.z;
-  if (xv >= Wv || y >= g.H) return;
-  const int x0 = xv * VEC;
-  const int64_t HW = (int64_t)g.H * g.W;
-  const float* fu = flow + (int64_t)n * 2 * HW + (int64_t)y * g.W + x0;
-  const float* fv = fu + HW;
-  float u[VEC], v[VEC];
-  if constexpr (VEC == 4) {
-    const float4 a = ld_stream4(fu), b = ld_stream4(fv);
-    u[0] = a.x; u[1] = a.y; u[2] = a.z; u[3] = a.w;
-    v[0] = b.x; v[1] = b.y; v[2] = b.z; v[3] = b.w;
-  } else {
-    u[0] = __ldg(fu);
-    v[0] = __ldg(fv);
+  if (x >= g.W || y >= g.H) return;
+  const int HW = g.H * g.W;
+  const int o = y * g.W + x;
+  const float* fu = flow + (int64_t)n * 2 * HW + o;
+  const float u = __ldg(fu), v = __ldg(fu + HW);
+  float tx = 0.f, ty = 0.f;
+  if (BORDER) {
+    tx = __ldg(tab_x + x);
+    ty = __ldg(tab_y + y);
   }
-  const bool flex = (g.variant == B200VC_WARP_FLEX);
-  const float ty = flex ? 0.f : __ldg(tab_y + y);
-  Taps t[VEC];
-#pragma unroll
-  for (int k = 0; k < VEC; ++k) {
-    const float tx = flex ? 0.f : __ldg(tab_x + x0 + k);
-    float ix, iy;
-    coords(g, x0 + k, y, u[k], v[k], tx, ty, ix, iy);
-    t[k] = make_taps(ix, iy, g.H, g.W);
-  }
+  float ix, iy;
+  coords<VARIANT, ARITH0>(g, x, y, u, v, tx, ty, ix, iy);
+  const Taps t = make_taps<BORDER>(ix, iy, g.H, g.W);
   const float* ip = img + (int64_t)n * img_bs;
-  float* op = out + (int64_t)n * out_bs + (int64_t)y * g.W + x0;
-  for (int c = 0; c < C; ++c) {
-    const float* plane = ip + (int64_t)c * HW;
-    float r[VEC];
+  float* op = out + (int64_t)n * out_bs + o;
+  if (CT > 0) {
+    float r[CT > 0 ? CT : 1];
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) r[k] = sample(plane, t[k]);
-    if constexpr (VEC == 4) {
-      st_stream4(op + (int64_t)c * HW, make_float4(r[0], r[1], r[2], r[3]));
-    } else {
-      op[(int64_t)c * HW] = r[0];
-    }
+    for (int c = 0; c < CT; ++c) r[c] = sample<BORDER>(ip + (int64_t)c * HW, t);
+#pragma unroll
+    for (int c = 0; c < CT; ++c) op[(int64_t)c * HW] = r[c];
+  } else {
+#pragma unroll 4
+    for (int c = 0; c < C; ++c) op[(int64_t)c * HW] = sample<BORDER>(ip + (int64_t)c * HW, t);
   }
 }
 
@@ -180,71 +199,62 @@ __device__ __forceinline__ float up4_value(const Up4& uy, const Up4& ux, float a
   return __fmaf_rn(uy.l0, top, __fmul_rn(uy.l1, bot));
 }
 
+// CTA = 32 x 8 output pixels.  The quarter-resolution flow (mv x_hat + linear-motion prior, m.py:56,58) that the
+// tile's x4 upsample touches -- at most 10 x 4 points x 4 channels -- is summed once into shared memory; every
+// pixel then reads its four corners from there (warp-wide broadcasts) instead of 32 global loads.
+constexpr int kQW = 10, kQH = 4;
+template <bool ARITH0>
 __global__ void __launch_bounds__(kWarpThreads)
 warp2_lhbdc_kernel(const float* __restrict__ xb, const float* __restrict__ xa,
                    const float* __restrict__ flow_hat, const float* __restrict__ flow_ab,
                    const float* __restrict__ flow_ba, const float* __restrict__ tab_x,
                    const float* __restrict__ tab_y, float* __restrict__ out, float* __restrict__ flows_out,
                    int h4, int w4, WarpGeom g) {
-  constexpr int VEC = 4;
-  const int Wv = g.W / VEC;
-  const int xv = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int y = blockIdx.y * (kWarpThreads / 32) + (threadIdx.x >> 5);
+  __shared__ float s_q[4][kQH][kQW];
   const int n = blockIdx.z;
-  if (xv >= Wv || y >= g.H) return;
-  const int x0 = xv * VEC;
+  const int bx = blockIdx.x * 32, by = blockIdx.y * (kWarpThreads / 32);
   const int hh = g.H / 4, ww = g.W / 4;
-  const int64_t HW = (int64_t)g.H * g.W;
-  const int64_t q = (int64_t)h4 * w4;
-  const Up4 uy = up4_index(y, hh);
-  const float ty = __ldg(tab_y + y);
-  float* op = out + (int64_t)n * 6 * HW + (int64_t)y * g.W + x0;
+  const int q = h4 * w4;
+  // first quarter-res column / row the tile can touch (i0 of its first pixel)
+  const int qx0 = up4_index(bx, ww).i0, qy0 = up4_index(by, hh).i0;
+  if (threadIdx.x < 4 * kQH * kQW) {
+    const int ch = threadIdx.x / (kQH * kQW), r = (threadIdx.x / kQW) % kQH, c = threadIdx.x % kQW;
+    const int sy = min(qy0 + r, hh - 1), sx = min(qx0 + c, ww - 1);
+    // ch 0,1 = flow_cb (x, y) = x_hat[0:2] + flow_ab ; ch 2,3 = flow_ca = x_hat[2:4] + flow_ba
+    const float* pri = (ch < 2 ? flow_ab : flow_ba) + ((int64_t)n * 2 + (ch & 1)) * q;
+    const float* hat = flow_hat + ((int64_t)n * 4 + ch) * q;
+    s_q[ch][r][c] = __fadd_rn(__ldg(hat + sy * w4 + sx), __ldg(pri + sy * w4 + sx));
+  }
+  __syncthreads();
+  const int x = bx + (threadIdx.x & 31), y = by + (threadIdx.x >> 5);
+  if (x >= g.W || y >= g.H) return;
+  const int HW = g.H * g.W;
+  const int o = y * g.W + x;
+  const Up4 ux = up4_index(x, ww), uy = up4_index(y, hh);
+  const int cx0 = ux.i0 - qx0, cx1 = ux.i1 - qx0, cy0 = uy.i0 - qy0, cy1 = uy.i1 - qy0;
+  const float tx = __ldg(tab_x + x), ty = __ldg(tab_y + y);
+  const int arith = ARITH0 ? 0 : g.arith;
+  float* op = out + (int64_t)n * 6 * HW + o;
 #pragma unroll
   for (int dir = 0; dir < 2; ++dir) {
-    // quarter-res value = mv x_hat chunk + linear-motion prior (m.py:56,58), rounded once like torch's add
-    const float* hat = flow_hat + ((int64_t)n * 4 + dir * 2) * q;
-    const float* pri = (dir == 0 ? flow_ab : flow_ba) + (int64_t)n * 2 * q;
-    float u[VEC], v[VEC];
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) {
-      const Up4 ux = up4_index(x0 + k, ww);
-      const int o00 = uy.i0 * w4 + ux.i0, o01 = uy.i0 * w4 + ux.i1;
-      const int o10 = uy.i1 * w4 + ux.i0, o11 = uy.i1 * w4 + ux.i1;
-      float f[2];
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        const float* h = hat + ch * q;
-        const float* p = pri + ch * q;
-        const float a = __fadd_rn(__ldg(h + o00), __ldg(p + o00));
-        const float b = __fadd_rn(__ldg(h + o01), __ldg(p + o01));
-        const float c = __fadd_rn(__ldg(h + o10), __ldg(p + o10));
-        const float d = __fadd_rn(__ldg(h + o11), __ldg(p + o11));
-        f[ch] = up4_value(uy, ux, a, b, c, d, g.arith);
-      }
-      u[k] = f[0];
-      v[k] = f[1];
-    }
+    const float u = up4_value(uy, ux, s_q[2 * dir][cy0][cx0], s_q[2 * dir][cy0][cx1], s_q[2 * dir][cy1][cx0],
+                              s_q[2 * dir][cy1][cx1], arith);
+    const float v = up4_value(uy, ux, s_q[2 * dir + 1][cy0][cx0], s_q[2 * dir + 1][cy0][cx1],
+                              s_q[2 * dir + 1][cy1][cx0], s_q[2 * dir + 1][cy1][cx1], arith);
     if (flows_out != nullptr) {
-      float* fo = flows_out + ((int64_t)n * 4 + dir * 2) * HW + (int64_t)y * g.W + x0;
-      st_stream4(fo, make_float4(u[0], u[1], u[2], u[3]));
-      st_stream4(fo + HW, make_float4(v[0], v[1], v[2], v[3]));
+      float* fo = flows_out + ((int64_t)n * 4 + dir * 2) * HW + o;
+      fo[0] = u;
+      fo[HW] = v;
     }
-    Taps t[VEC];
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) {
-      float ix, iy;
-      coords(g, x0 + k, y, u[k], v[k], __ldg(tab_x + x0 + k), ty, ix, iy);
-      t[k] = make_taps(ix, iy, g.H, g.W);
-    }
+    float ix, iy;
+    coords<B200VC_WARP_LHBDC, ARITH0>(g, x, y, u, v, tx, ty, ix, iy);
+    const Taps t = make_taps<true>(ix, iy, g.H, g.W);
     const float* ip = (dir == 0 ? xb : xa) + (int64_t)n * 3 * HW;
+    float r[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float* plane = ip + (int64_t)c * HW;
-      float r[VEC];
+    for (int c = 0; c < 3; ++c) r[c] = sample<true>(ip + (int64_t)c * HW, t);
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) r[k] = sample(plane, t[k]);
-      st_stream4(op + (int64_t)(dir * 3 + c) * HW, make_float4(r[0], r[1], r[2], r[3]));
-    }
+    for (int c = 0; c < 3; ++c) op[(int64_t)(dir * 3 + c) * HW] = r[c];
   }
 }
 
@@ -266,8 +276,6 @@ static WarpGeom make_geom(int H, int W, int variant, int arith) {
   return g;
 }
 
-static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
-
 }  // namespace b200vc
 
 using namespace b200vc;
@@ -282,17 +290,32 @@ extern "C" int b200vc_warp_f32(const float* img, int64_t img_bs, const float* fl
   B200VC_REQUIRE((int64_t)H * W < (1ll << 31), "warp_f32: plane too large");
   B200VC_REQUIRE(N <= 65535, "warp_f32: N too large");
   const WarpGeom g = make_geom(H, W, variant, arith);
-  const int64_t HW = (int64_t)H * W;
-  const bool vec = (W % 4 == 0) && aligned16(flow) && aligned16(out) && (out_bs % 4 == 0) && (HW % 4 == 0);
   cudaStream_t st = (cudaStream_t)stream;
   const int rows = kWarpThreads / 32;
-  if (vec) {
-    dim3 grid((W / 4 + 31) / 32, (H + rows - 1) / rows, N);
-    warp_kernel<4><<<grid, kWarpThreads, 0, st>>>(img, img_bs, flow, tab_x, tab_y, out, out_bs, C, g);
-  } else {
-    dim3 grid((W + 31) / 32, (H + rows - 1) / rows, N);
-    warp_kernel<1><<<grid, kWarpThreads, 0, st>>>(img, img_bs, flow, tab_x, tab_y, out, out_bs, C, g);
+  dim3 grid((W + 31) / 32, (H + rows - 1) / rows, N);
+#define B200VC_WARP_ARGS img, img_bs, flow, tab_x, tab_y, out, out_bs, C, g
+#define B200VC_WARP_LAUNCH(CT)                                                                            \
+  do {                                                                                                    \
+    if (arith != 0) {                                                                                     \
+      if (variant == B200VC_WARP_LHBDC) warp_kernel<0, 0, false><<<grid, kWarpThreads, 0, st>>>(B200VC_WARP_ARGS); \
+      else if (variant == B200VC_WARP_FLEX) warp_kernel<0, 1, false><<<grid, kWarpThreads, 0, st>>>(B200VC_WARP_ARGS); \
+      else warp_kernel<0, 2, false><<<grid, kWarpThreads, 0, st>>>(B200VC_WARP_ARGS);                     \
+    } else if (variant == B200VC_WARP_LHBDC)                                                              \
+      warp_kernel<CT, 0, true><<<grid, kWarpThreads, 0, st>>>(B200VC_WARP_ARGS);                          \
+    else if (variant == B200VC_WARP_FLEX)                                                                 \
+      warp_kernel<CT, 1, true><<<grid, kWarpThreads, 0, st>>>(B200VC_WARP_ARGS);                          \
+    else                                                                                                  \
+      warp_kernel<CT, 2, true><<<grid, kWarpThreads, 0, st>>>(B200VC_WARP_ARGS);                          \
+  } while (0)
+  switch (C) {
+    case 1: B200VC_WARP_LAUNCH(1); break;
+    case 2: B200VC_WARP_LAUNCH(2); break;
+    case 3: B200VC_WARP_LAUNCH(3); break;
+    case 4: B200VC_WARP_LAUNCH(4); break;
+    default: B200VC_WARP_LAUNCH(0); break;
   }
+#undef B200VC_WARP_LAUNCH
+#undef B200VC_WARP_ARGS
   return check_launch("warp_f32");
 }
 
@@ -305,13 +328,15 @@ extern "C" int b200vc_warp2_lhbdc_f32(const float* x_before, const float* x_afte
   B200VC_REQUIRE(N > 0 && N <= 65535 && H > 0 && W > 0, "warp2_lhbdc_f32: bad shape");
   B200VC_REQUIRE(H % 4 == 0 && W % 4 == 0, "warp2_lhbdc_f32: H, W must be multiples of 4 (got %d x %d)", H, W);
   B200VC_REQUIRE(h4 >= H / 4 && w4 >= W / 4, "warp2_lhbdc_f32: quarter-res tensors smaller than the crop");
-  B200VC_REQUIRE(aligned16(out) && (flows_out == nullptr || aligned16(flows_out)),
-                 "warp2_lhbdc_f32: outputs must be 16-byte aligned");
   B200VC_REQUIRE((int64_t)H * W < (1ll << 31), "warp2_lhbdc_f32: plane too large");
   const WarpGeom g = make_geom(H, W, B200VC_WARP_LHBDC, arith);
   const int rows = kWarpThreads / 32;
-  dim3 grid((W / 4 + 31) / 32, (H + rows - 1) / rows, N);
-  warp2_lhbdc_kernel<<<grid, kWarpThreads, 0, (cudaStream_t)stream>>>(
-      x_before, x_after, flow_hat, flow_ab, flow_ba, tab_x, tab_y, out, flows_out, h4, w4, g);
+  dim3 grid((W + 31) / 32, (H + rows - 1) / rows, N);
+  if (arith == 0)
+    warp2_lhbdc_kernel<true><<<grid, kWarpThreads, 0, (cudaStream_t)stream>>>(
+        x_before, x_after, flow_hat, flow_ab, flow_ba, tab_x, tab_y, out, flows_out, h4, w4, g);
+  else
+    warp2_lhbdc_kernel<false><<<grid, kWarpThreads, 0, (cudaStream_t)stream>>>(
+        x_before, x_after, flow_hat, flow_ab, flow_ba, tab_x, tab_y, out, flows_out, h4, w4, g);
   return check_launch("warp2_lhbdc_f32");
 }
