@@ -121,7 +121,8 @@ B200VC_API int b200vc_gdn_prepare_f32(const float* beta, const float* gamma, flo
                            float pedestal, float* params_out, int C, void* stream);
 /*   x, out [N,C,HW]; addend (nullable) [N,C,HW] is added to the result (the residual-block skip,
  *   compressai ResidualBlockWithStride/ResidualBlockUpsample `out += identity`); out must not alias x or addend.
- *   out_i = x_i * rsqrt(beta_i + sum_j gamma_ij x_j^2)    (inverse != 0: * sqrt).
+ *   out_i = x_i * rsqrt(beta_i + sum_j gamma_ij x_j^2)    (inverse == 1: * sqrt; inverse == 2, diagnostics:
+ *   out_i = the norm beta_i + sum_j gamma_ij x_j^2 itself).
  *   impl: 0 = auto, 1 = CUDA-core fp32 kernel (any C % 32 == 0), 2 = tcgen05 3xTF32 kernel (C == 128).
  */
 B200VC_API int b200vc_gdn_f32(const float* x, const float* params, const float* addend, float* out, int N, int C,

@@ -31,6 +31,42 @@ params = modules.gdn_params(p)
 torch.cuda.synchronize()
 print("params ready", flush=True)
 
+# ---- structural diagnostics: gamma = I, beta = 0, debug mode 2 returns norm = gamma @ x^2 ------------------
+def manual_params(gam):
+    Cc = gam.shape[0]
+    hi = gam.clone()
+    return torch.cat([torch.zeros(Cc), gam.flatten(), gam.t().contiguous().flatten(), hi.flatten(),
+                      torch.zeros(Cc * Cc)]).cuda()
+
+
+def raw_norm(x, prm, impl):
+    out = torch.empty_like(x)
+    from b200vc import _lib
+    lib = _lib.load()
+    rc = lib.b200vc_gdn_f32(x.data_ptr(), prm.data_ptr(), None, out.data_ptr(), x.shape[0], x.shape[1],
+                            x.shape[2] * x.shape[3], 2, impl, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, _lib.last_error()
+    torch.cuda.synchronize()
+    return out
+
+
+eye = manual_params(torch.eye(C))
+xs = torch.zeros(1, C, 8, 16).cuda()  # 128 positions = 2 tiles
+probes = [(0, 0), (1, 0), (5, 3), (9, 37), (77, 64), (127, 127)]
+for (j0, p0) in probes:
+    xs.zero_()
+    xs.view(C, 128)[j0, p0] = 2.0
+    nz = raw_norm(xs, eye, 2).view(C, 128).nonzero().tolist()
+    print(f"one-hot x[j={j0}, p={p0}] with gamma=I -> norm nonzero at {nz[:6]} (expect [[{j0}, {p0}]])", flush=True)
+perm = torch.randperm(C, generator=g)
+pm = torch.zeros(C, C)
+pm[torch.arange(C), perm] = 1.0  # norm[i] = x^2[perm[i]]
+xr = torch.randn(1, C, 8, 16, generator=g).cuda()
+got = raw_norm(xr, manual_params(pm), 2).view(C, 128)
+want = (xr.view(C, 128) ** 2)[perm.cuda()]
+print("gamma = permutation: max abs err", (got - want).abs().max().item(),
+      "(tf32-rounded x^2 expected: ~1e-3 rel since lo image is zero)", flush=True)
+
 for (N, H, W) in [(1, 8, 8), (1, 5, 8), (1, 16, 20), (2, 33, 44), (1, 68, 120), (3, 136, 240), (1, 544, 960)]:
     scale = torch.exp(torch.empty(1, C, 1, 1).uniform_(-2.3, 2.3, generator=g))
     x = (torch.randn(N, C, H, W, generator=g) * scale).cuda()

@@ -141,7 +141,7 @@ gdn_fp32_kernel(const float* __restrict__ x, const float* __restrict__ params, c
         for (int e = 0; e < 4; ++e) {
           const float nrm = __fadd_rn(acc[r][g * 4 + e], beta[r]);
           const float f = inverse ? sqrtf(nrm) : rsqrtf(nrm);
-          o[e] = __fmul_rn(xe[e], f);
+          o[e] = inverse == 2 ? nrm : __fmul_rn(xe[e], f);
         }
         if (vec_ok) {
           if (p < HW) {

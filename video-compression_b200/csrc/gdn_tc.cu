@@ -11,8 +11,9 @@
 //   * A operand  = gamma (M = 128 output channels x K = 128 input channels), resident in TMEM for the whole
 //     kernel (hi: columns [0,128), lo: [128,256)), written once with tcgen05.st.
 //   * B operand  = x^2 tile (K = 128 channels x N = 64 positions), MN-major (positions contiguous, exactly the
-//     NCHW layout), SWIZZLE_128B.  TMA loads the raw x tile as two [128 x 32] boxes whose 128B-swizzled image
-//     *is* the canonical MN-major UMMA layout, so the square/split pass is a pure elementwise smem->smem copy.
+//     NCHW layout), SWIZZLE_128B_BASE32B.  TMA (SWIZZLE_128B_ATOM_32B) loads the raw x tile as two [128 x 32]
+//     boxes whose swizzled image *is* the canonical MN-major UMMA layout, so the square/split pass is a pure
+//     elementwise smem->smem copy with no index arithmetic.
 //   * D          = 128 lanes (channels) x 64 columns (positions) fp32 in TMEM, double buffered.
 //   * warp 0: TMA producer | warp 1: TMEM alloc + MMA issuer (48 tcgen05.mma per tile) |
 //     warps 2-5: square + hi/lo split | warps 6-9: epilogue (tcgen05.ld -> +beta -> rsqrt/sqrt -> * x ->
@@ -85,15 +86,19 @@ __device__ __forceinline__ void tma_store_commit_and_wait_read() {
 }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-// SWIZZLE_128B, MN-major B operand: LBO = distance between the two 32-position atoms, SBO = distance between
-// groups of 8 channels (cute/atom/mma_traits_sm100.hpp make_umma_desc<Major::MN>).
+// MN-major TF32 operand: the only legal smem layout is SWIZZLE_128B_BASE32B (cutlass sm100_common.inl:
+// "for mn-major tf32 operands, SW128_32B is the only available smem layout"): rows of 128 B (32 positions),
+// 32-byte chunk index XOR (row & 3), canonical ((8,n),(4,k)):((1,LBO),(8,SBO)) in 16-byte units
+// (cute/atom/mma_traits_sm100.hpp make_umma_desc<Major::MN>).  LBO = distance between the two 32-position
+// atoms, SBO = distance between groups of 4 channels.  TMA produces exactly this image with
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
 __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
   d |= (uint64_t)((kHalfBytes >> 4) & 0x3FFF) << 16;  // leading byte offset  (16 KB)
-  d |= (uint64_t)((1024 >> 4) & 0x3FFF) << 32;        // stride byte offset   (8 rows x 128 B)
+  d |= (uint64_t)((512 >> 4) & 0x3FFF) << 32;         // stride byte offset   (4 rows x 128 B)
   d |= (uint64_t)1 << 46;                              // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                              // SWIZZLE_128B
+  d |= (uint64_t)1 << 61;                              // SWIZZLE_128B_BASE32B
   return d;
 }
 // kind::tf32, D = F32, A = B = TF32, A K-major (TMEM), B MN-major, N = 64, M = 128.
@@ -291,14 +296,15 @@ gdn_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + kColD + kTileP * s + 32 * h, v);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          float4* slot = raw4 + h * (kHalfBytes / 16) + i * 8 + (c ^ (i & 7));
+          // logical 16-byte chunk c of row i lives at 32-byte chunk ((c >> 1) ^ (i & 3)), same half
+          float4* slot = raw4 + h * (kHalfBytes / 16) + i * 8 + ((((c >> 1) ^ (i & 3)) << 1) | (c & 1));
           const float4 x = *slot;
           float nr[4], o[4];
           const float xe[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             nr[e] = __fadd_rn(__uint_as_float(v[4 * c + e]), beta);
-            o[e] = __fmul_rn(xe[e], inverse ? sqrtf(nr[e]) : rsqrtf(nr[e]));
+            o[e] = inverse == 2 ? nr[e] : __fmul_rn(xe[e], inverse ? sqrtf(nr[e]) : rsqrtf(nr[e]));
           }
           if (arow != nullptr) {
             const int64_t p = (int64_t)p0 + 32 * h + 4 * c;
@@ -356,7 +362,7 @@ static bool make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t 
   cuuint32_t box[2] = {32, (cuuint32_t)kC};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
