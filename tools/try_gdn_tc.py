@@ -84,6 +84,7 @@ for (N, H, W) in [(1, 8, 8), (1, 5, 8), (1, 16, 20), (2, 33, 44), (1, 68, 120), 
               f"finite={torch.isfinite(got).all().item()}", flush=True)
 
 flush_buf = torch.empty(256 * 1024 * 1024 // 4, device="cuda")
+print("B200VC_GDN_TC_CFG =", os.environ.get("B200VC_GDN_TC_CFG", "0"))
 for (N, H, W) in [(1, 544, 960), (4, 544, 960), (1, 272, 480), (1, 136, 240)]:
     x = torch.randn(N, C, H, W, device="cuda")
     for impl in (1, 2):

@@ -7,19 +7,22 @@
 // to TF32 (cvt.rna) and lo/glo the exact remainders; D = ghi*hi + ghi*lo + glo*hi, fp32 accumulation in TMEM
 // (dropped term glo*lo ~ 2^-22 relative).  See DESIGN.md for the error budget.
 //
-// Mapping (one persistent CTA per SM, 320 threads, warp-specialised):
+// Mapping (one persistent CTA per SM, 448 threads, warp-specialised, mbarrier pipelines):
 //   * A operand  = gamma (M = 128 output channels x K = 128 input channels), resident in TMEM for the whole
 //     kernel (hi: columns [0,128), lo: [128,256)), written once with tcgen05.st.
 //   * B operand  = x^2 tile (K = 128 channels x N = 64 positions), MN-major (positions contiguous, exactly the
 //     NCHW layout), SWIZZLE_128B_BASE32B.  TMA (SWIZZLE_128B_ATOM_32B) loads the raw x tile as two [128 x 32]
 //     boxes whose swizzled image *is* the canonical MN-major UMMA layout, so the square/split pass is a pure
 //     elementwise smem->smem copy with no index arithmetic.
-//   * D          = 128 lanes (channels) x 64 columns (positions) fp32 in TMEM, double buffered.
-//   * warp 0: TMA producer | warp 1: TMEM alloc + MMA issuer (48 tcgen05.mma per tile) |
-//     warps 2-5: square + hi/lo split | warps 6-9: epilogue (tcgen05.ld -> +beta -> rsqrt/sqrt -> * x ->
-//     in-place into the raw tile -> TMA store).
+//   * D          = 128 lanes (channels) x 64 columns (positions) fp32 in TMEM; two accumulators per tile
+//     (D1 = ghi*hi, D2 = the small cross terms), double buffered: 256 + 2*128 = all 512 TMEM columns.
+//   * warp 0: TMA producer (ring of R raw tiles) | warp 1: TMEM alloc + MMA issuer (48 tcgen05.mma per tile) |
+//     warps 2-5: square + hi/lo split (ring of A operand pairs) | warps 6-13: epilogue (tcgen05.ld ->
+//     D1+D2+beta -> rsqrt/sqrt -> * x -> in place into the raw tile -> TMA store; the raw slot is released
+//     one tile later so the store drains behind the next tile's epilogue).
 // Algorithmic HBM traffic: 2*128*4 B per position (+128*4 with addend); 3 * 2*128*128 tensor flop per position.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -29,14 +32,24 @@ namespace tc {
 
 constexpr int kC = 128;            // channels (UMMA M and K)
 constexpr int kTileP = 64;         // positions per tile (UMMA N)
-constexpr int kStages = 2;
 constexpr int kHalfBytes = kC * 32 * 4;          // one [128 x 32] fp32 box = 16 KB
 constexpr int kTileBytes = 2 * kHalfBytes;       // 32 KB
-constexpr int kStageBytes = 3 * kTileBytes;      // raw + hi + lo
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int kThreads = 320;
+constexpr int kEpiWarps = 8;                     // 2 per TMEM lane quarter (one per 32-column half)
+constexpr int kThreads = (6 + kEpiWarps) * 32;   // 448
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kColGhi = 0, kColGlo = 128, kColD = 256;
+// TMEM columns: gamma hi | gamma lo | 2 accumulator stages x (D1: ghi*hi, D2: ghi*lo + glo*hi)
+constexpr uint32_t kColGhi = 0, kColGlo = 128, kColD = 256, kColDStage = 2 * kTileP;
+
+// Ring depths: R raw tiles (TMA load .. TMA store), A hi/lo operand pairs (transform .. MMA done).
+template <int R, int A>
+struct Cfg {
+  static constexpr int kRaw = R, kAb = A;
+  static constexpr int kRawOff = 0;
+  static constexpr int kAbOff = R * kTileBytes;              // A x (hi | lo)
+  static constexpr int kBarOff = kAbOff + A * 2 * kTileBytes;
+  static constexpr int kNumBars = 2 * R + 2 * A + 4;
+  static constexpr int kSmemBytes = kBarOff + 8 * kNumBars + 16 + 1024 /*alignment slack*/;
+};
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -149,32 +162,41 @@ __device__ __forceinline__ float to_tf32_rna(float v) {
 }
 
 // params layout (gdn.cu): [0,C) beta | gamma | gammaT | hi[i][j] (C*C) | lo[i][j] (C*C)
+template <class CFG>
 __global__ void __launch_bounds__(kThreads, 1)
 gdn_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_out,
               const float* __restrict__ params, const float* __restrict__ addend, int64_t HW,
               int tiles_per_sample, int total_tiles, int inverse) {
+  constexpr int R = CFG::kRaw, A = CFG::kAb;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  // per stage: raw | hi | lo
-  auto raw_addr = [&](int s) { return smem_base + s * kStageBytes; };
-  auto hi_addr = [&](int s) { return smem_base + s * kStageBytes + kTileBytes; };
-  auto lo_addr = [&](int s) { return smem_base + s * kStageBytes + 2 * kTileBytes; };
-  const uint32_t bar_base = smem_base + kStages * kStageBytes;
-  auto raw_full = [&](int s) { return bar_base + 8 * s; };
-  auto ab_full = [&](int s) { return bar_base + 16 + 8 * s; };
-  auto mma_done = [&](int s) { return bar_base + 32 + 8 * s; };
-  auto raw_empty = [&](int s) { return bar_base + 48 + 8 * s; };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + kStages * kStageBytes + 64);
+  auto raw_addr = [&](int r) { return smem_base + CFG::kRawOff + r * kTileBytes; };
+  auto hi_addr = [&](int a) { return smem_base + CFG::kAbOff + a * 2 * kTileBytes; };
+  auto lo_addr = [&](int a) { return smem_base + CFG::kAbOff + a * 2 * kTileBytes + kTileBytes; };
+  const uint32_t bar_base = smem_base + CFG::kBarOff;
+  auto raw_full = [&](int r) { return bar_base + 8 * r; };
+  auto raw_empty = [&](int r) { return bar_base + 8 * (R + r); };
+  auto ab_full = [&](int a) { return bar_base + 8 * (2 * R + a); };
+  auto ab_empty = [&](int a) { return bar_base + 8 * (2 * R + A + a); };
+  auto d_full = [&](int d) { return bar_base + 8 * (2 * R + 2 * A + d); };
+  auto d_empty = [&](int d) { return bar_base + 8 * (2 * R + 2 * A + 2 + d); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + CFG::kBarOff + 8 * CFG::kNumBars);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(raw_full(s), 1);
-      mbar_init(ab_full(s), 128);
-      mbar_init(mma_done(s), 1);
-      mbar_init(raw_empty(s), 1);
+    for (int r = 0; r < R; ++r) {
+      mbar_init(raw_full(r), 1);
+      mbar_init(raw_empty(r), 1);
+    }
+    for (int a = 0; a < A; ++a) {
+      mbar_init(ab_full(a), 128);
+      mbar_init(ab_empty(a), 1);
+    }
+    for (int d = 0; d < 2; ++d) {
+      mbar_init(d_full(d), 1);
+      mbar_init(d_empty(d), kEpiWarps * 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
@@ -191,23 +213,22 @@ gdn_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  // gamma hi/lo -> TMEM (lane = output channel i, column = input channel j), by the four epilogue warps
+  // gamma hi/lo -> TMEM (lane = output channel i, column = input channel j), by the epilogue warps:
+  // warp w owns lane quarter (w & 3); the two warps of a quarter take hi and lo respectively.
   if (warp >= 6) {
-    const int q = warp & 3;
+    const int q = warp & 3, which = (warp - 6) >> 2;
     const int i = 32 * q + lane;
-    const float* hi = params + kC + 2 * kC * kC + (int64_t)i * kC;
-    const float* lo = hi + kC * kC;
+    const float* src_row = params + kC + 2 * kC * kC + (int64_t)which * kC * kC + (int64_t)i * kC;
 #pragma unroll 1
-    for (int part = 0; part < 8; ++part) {
-      const float* src = (part < 4 ? hi : lo) + (part & 3) * 32;
+    for (int part = 0; part < 4; ++part) {
       uint32_t v[32];
 #pragma unroll
       for (int e = 0; e < 32; e += 4) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(src + e));
+        const float4 t = __ldg(reinterpret_cast<const float4*>(src_row + part * 32 + e));
         v[e] = __float_as_uint(t.x); v[e + 1] = __float_as_uint(t.y);
         v[e + 2] = __float_as_uint(t.z); v[e + 3] = __float_as_uint(t.w);
       }
-      tmem_st32(tmem + ((uint32_t)(32 * q) << 16) + (part < 4 ? kColGhi : kColGlo) + (part & 3) * 32, v);
+      tmem_st32(tmem + ((uint32_t)(32 * q) << 16) + (which ? kColGlo : kColGhi) + part * 32, v);
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   }
@@ -220,13 +241,13 @@ gdn_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     if (lane == 0) {
       int k = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++k) {
-        const int s = k & 1, ph = (k >> 1) & 1;
+        const int r = k % R, ph = (k / R) & 1;
         const int row0 = (tile / tiles_per_sample) * kC;
         const int p0 = (tile % tiles_per_sample) * kTileP;
-        mbar_wait(raw_empty(s), ph ^ 1);
-        mbar_arrive_expect_tx(raw_full(s), kTileBytes);
-        tma_load_2d(raw_addr(s), &map_x, p0, row0, raw_full(s));
-        tma_load_2d(raw_addr(s) + kHalfBytes, &map_x, p0 + 32, row0, raw_full(s));
+        mbar_wait(raw_empty(r), ph ^ 1);
+        mbar_arrive_expect_tx(raw_full(r), kTileBytes);
+        tma_load_2d(raw_addr(r), &map_x, p0, row0, raw_full(r));
+        tma_load_2d(raw_addr(r) + kHalfBytes, &map_x, p0 + 32, row0, raw_full(r));
       }
     }
   } else if (warp == 1) {
@@ -234,20 +255,24 @@ gdn_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     if (lane == 0) {
       int k = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++k) {
-        const int s = k & 1, ph = (k >> 1) & 1;
-        mbar_wait(ab_full(s), ph);
+        const int a = k % A, pa = (k / A) & 1, d = k & 1, pd = (k >> 1) & 1;
+        mbar_wait(ab_full(a), pa);
+        mbar_wait(d_empty(d), pd ^ 1);
         tc_fence_after();
-        const uint32_t d = tmem + kColD + kTileP * s;
-#pragma unroll 1
-        for (int pass = 0; pass < 3; ++pass) {
-          // pass 0: ghi * hi   pass 1: ghi * lo   pass 2: glo * hi
-          const uint32_t a0 = tmem + (pass == 2 ? kColGlo : kColGhi);
-          const uint32_t b0 = (pass == 1) ? lo_addr(s) : hi_addr(s);
+        // Two accumulators: the tensor core's fp32 accumulation truncates, so the 32 small cross-term steps
+        // go to their own accumulator and never disturb the 16-step main sum; the epilogue adds them (RN).
+        const uint32_t d1 = tmem + kColD + kColDStage * d, d2 = d1 + kTileP;
 #pragma unroll
-          for (int g = 0; g < kC / 8; ++g)
-            umma_tf32_ts(d, a0 + 8 * g, make_b_desc(b0 + g * 1024), (pass | g) != 0 ? 1u : 0u);
-        }
-        umma_commit(mma_done(s));
+        for (int g = 0; g < kC / 8; ++g)   // D1  = ghi * hi
+          umma_tf32_ts(d1, tmem + kColGhi + 8 * g, make_b_desc(hi_addr(a) + g * 1024), g != 0 ? 1u : 0u);
+#pragma unroll
+        for (int g = 0; g < kC / 8; ++g)   // D2  = ghi * lo
+          umma_tf32_ts(d2, tmem + kColGhi + 8 * g, make_b_desc(lo_addr(a) + g * 1024), g != 0 ? 1u : 0u);
+#pragma unroll
+        for (int g = 0; g < kC / 8; ++g)   // D2 += glo * hi
+          umma_tf32_ts(d2, tmem + kColGlo + 8 * g, make_b_desc(hi_addr(a) + g * 1024), 1u);
+        umma_commit(ab_empty(a));  // hi/lo pair consumed
+        umma_commit(d_full(d));    // accumulators ready
       }
     }
   } else if (warp < 6) {
@@ -255,11 +280,12 @@ gdn_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     const int t = threadIdx.x - 64;
     int k = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++k) {
-      const int s = k & 1, ph = (k >> 1) & 1;
-      mbar_wait(raw_full(s), ph);
-      const float4* raw4 = reinterpret_cast<const float4*>(smem_gen + s * kStageBytes);
-      float4* hi4 = reinterpret_cast<float4*>(smem_gen + s * kStageBytes + kTileBytes);
-      float4* lo4 = reinterpret_cast<float4*>(smem_gen + s * kStageBytes + 2 * kTileBytes);
+      const int r = k % R, pr = (k / R) & 1, a = k % A, pa = (k / A) & 1;
+      mbar_wait(raw_full(r), pr);
+      mbar_wait(ab_empty(a), pa ^ 1);
+      const float4* raw4 = reinterpret_cast<const float4*>(smem_gen + CFG::kRawOff + r * kTileBytes);
+      float4* hi4 = reinterpret_cast<float4*>(smem_gen + CFG::kAbOff + a * 2 * kTileBytes);
+      float4* lo4 = hi4 + kTileBytes / 16;
 #pragma unroll 4
       for (int it = 0; it < kTileBytes / 16 / 128; ++it) {
         const int idx = it * 128 + t;
@@ -272,62 +298,70 @@ gdn_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         lo4[idx] = l;
       }
       fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
-      mbar_arrive(ab_full(s));
+      mbar_arrive(ab_full(a));
     }
   } else {
-    // ------------------------------------------------------------------ epilogue
-    const int q = warp & 3;
-    const int i = 32 * q + lane;  // output channel == TMEM lane
+    // ------------------------------------------------------------------ epilogue (8 warps)
+    const int q = warp & 3;           // TMEM lane quarter this warp may access
+    const int h = (warp - 6) >> 2;    // 32-column (= 32-position) half of the tile
+    const int i = 32 * q + lane;      // output channel == TMEM lane
     const float beta = __ldg(params + i);
     const bool leader = (threadIdx.x == 6 * 32);
     int k = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++k) {
-      const int s = k & 1, ph = (k >> 1) & 1;
-      const int n = tile / tiles_per_sample;
-      const int row0 = n * kC;
+      const int r = k % R, d = k & 1, pd = (k >> 1) & 1;
+      const int row0 = (tile / tiles_per_sample) * kC;
       const int p0 = (tile % tiles_per_sample) * kTileP;
-      mbar_wait(mma_done(s), ph);
+      mbar_wait(d_full(d), pd);
       tc_fence_after();
-      float4* raw4 = reinterpret_cast<float4*>(smem_gen + s * kStageBytes);
-      const float* arow = addend ? addend + ((int64_t)row0 + i) * HW : nullptr;
-#pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
-        uint32_t v[32];
-        tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + kColD + kTileP * s + 32 * h, v);
+      uint32_t v1[32], v2[32];
+      const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + kColD + kColDStage * d + 32 * h;
+      tmem_ld32(taddr, v1);
+      tmem_ld32(taddr + kTileP, v2);
+      tc_fence_before();
+      mbar_arrive(d_empty(d));  // accumulators drained: the MMA warp may start tile k+2
+      float4* raw4 = reinterpret_cast<float4*>(smem_gen + CFG::kRawOff + r * kTileBytes) + h * (kHalfBytes / 16) + i * 8;
+      const float* arow = addend ? addend + ((int64_t)row0 + i) * HW + p0 + 32 * h : nullptr;
+      const int64_t pbase = (int64_t)p0 + 32 * h;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          // logical 16-byte chunk c of row i lives at 32-byte chunk ((c >> 1) ^ (i & 3)), same half
-          float4* slot = raw4 + h * (kHalfBytes / 16) + i * 8 + ((((c >> 1) ^ (i & 3)) << 1) | (c & 1));
-          const float4 x = *slot;
-          float nr[4], o[4];
-          const float xe[4] = {x.x, x.y, x.z, x.w};
+      for (int c = 0; c < 8; ++c) {
+        // logical 16-byte chunk c of row i lives at 32-byte chunk ((c >> 1) ^ (i & 3)), same half
+        float4* slot = raw4 + ((((c >> 1) ^ (i & 3)) << 1) | (c & 1));
+        const float4 x = *slot;
+        float o[4];
+        const float xe[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            nr[e] = __fadd_rn(__uint_as_float(v[4 * c + e]), beta);
-            o[e] = inverse == 2 ? nr[e] : __fmul_rn(xe[e], inverse ? sqrtf(nr[e]) : rsqrtf(nr[e]));
-          }
-          if (arow != nullptr) {
-            const int64_t p = (int64_t)p0 + 32 * h + 4 * c;
-            if (p < HW) {
-              const float4 a4 = *reinterpret_cast<const float4*>(arow + p);
-              o[0] = __fadd_rn(o[0], a4.x); o[1] = __fadd_rn(o[1], a4.y);
-              o[2] = __fadd_rn(o[2], a4.z); o[3] = __fadd_rn(o[3], a4.w);
-            }
-          }
-          *slot = make_float4(o[0], o[1], o[2], o[3]);
+        for (int e = 0; e < 4; ++e) {
+          const float acc = __fadd_rn(__uint_as_float(v1[4 * c + e]), __uint_as_float(v2[4 * c + e]));
+          const float nr = __fadd_rn(acc, beta);
+          o[e] = inverse == 2 ? nr : __fmul_rn(xe[e], inverse ? sqrtf(nr) : rsqrtf(nr));
+        }
+        if (arow != nullptr && pbase + 4 * c < HW) {
+          const float4 a4 = *reinterpret_cast<const float4*>(arow + 4 * c);
+          o[0] = __fadd_rn(o[0], a4.x); o[1] = __fadd_rn(o[1], a4.y);
+          o[2] = __fadd_rn(o[2], a4.z); o[3] = __fadd_rn(o[3], a4.w);
+        }
+        *slot = make_float4(o[0], o[1], o[2], o[3]);
+      }
+      fence_proxy_async();  // result tile (generic writes) -> visible to the TMA store
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (leader) {
+        tma_store_2d(&map_out, raw_addr(r), p0, row0);
+        if ((int64_t)p0 + 32 < HW) tma_store_2d(&map_out, raw_addr(r) + kHalfBytes, p0 + 32, row0);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        // release the PREVIOUS tile's raw slot once its store has finished reading shared memory; the store
+        // just issued keeps draining while the next tile's epilogue runs
+        if (k > 0) {
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          mbar_arrive(raw_empty((k - 1) % R));
         }
       }
-      tc_fence_before();
-      fence_proxy_async();  // result tile (generic writes) -> visible to the TMA store
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (leader) {
-        tma_store_2d(&map_out, raw_addr(s), p0, row0);
-        if ((int64_t)p0 + 32 < HW) tma_store_2d(&map_out, raw_addr(s) + kHalfBytes, p0 + 32, row0);
-        tma_store_commit_and_wait_read();
-        mbar_arrive(raw_empty(s));
-      }
     }
-    if (leader) tma_store_wait_all();
+    if (leader && k > 0) {
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      mbar_arrive(raw_empty((k - 1) % R));
+      tma_store_wait_all();
+    }
   }
 
   tc_fence_before();
@@ -367,6 +401,25 @@ static bool make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t 
   return r == CUDA_SUCCESS;
 }
 
+template <class CFG>
+static int launch_cfg(const CUtensorMap& map_x, const CUtensorMap& map_out, const float* params, const float* addend,
+                      int64_t HW, int tps, int total, int inverse, int grid, cudaStream_t st) {
+  static bool configured[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !configured[dev]) {
+    if (cudaFuncSetAttribute(gdn_tc_kernel<CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::kSmemBytes) !=
+        cudaSuccess) {
+      set_error("gdn_f32: cannot reserve %d B of shared memory", CFG::kSmemBytes);
+      (void)cudaGetLastError();
+      return B200VC_EUNSUPPORTED;
+    }
+    configured[dev] = true;
+  }
+  gdn_tc_kernel<CFG><<<grid, kThreads, CFG::kSmemBytes, st>>>(map_x, map_out, params, addend, HW, tps, total, inverse);
+  return check_launch("gdn_f32(tcgen05)");
+}
+
 }  // namespace tc
 
 int launch_gdn_tc(const float* x, const float* params, const float* addend, float* out, int N, int C, int64_t HW,
@@ -381,17 +434,6 @@ int launch_gdn_tc(const float* x, const float* params, const float* addend, floa
     set_error("gdn_f32: cuTensorMapEncodeTiled failed");
     return B200VC_EUNSUPPORTED;
   }
-  static bool configured[64] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev >= 0 && dev < 64 && !configured[dev]) {
-    if (cudaFuncSetAttribute(gdn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) {
-      set_error("gdn_f32: cannot reserve %d B of shared memory", kSmemBytes);
-      (void)cudaGetLastError();
-      return B200VC_EUNSUPPORTED;
-    }
-    configured[dev] = true;
-  }
   const int64_t tps = (HW + kTileP - 1) / kTileP;
   const int64_t total = tps * N;
   if (total >= (1ll << 31)) {
@@ -399,8 +441,15 @@ int launch_gdn_tc(const float* x, const float* params, const float* addend, floa
     return B200VC_EINVAL;
   }
   const int grid = (int)(total < sm_count() ? total : sm_count());
-  gdn_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(map_x, map_out, params, addend, HW, (int)tps, (int)total, inverse);
-  return check_launch("gdn_f32(tcgen05)");
+  static const int cfg = []() {
+    const char* e = getenv("B200VC_GDN_TC_CFG");
+    return e ? atoi(e) : 0;
+  }();
+  switch (cfg) {
+    case 1: return launch_cfg<Cfg<4, 1>>(map_x, map_out, params, addend, HW, (int)tps, (int)total, inverse, grid, st);
+    case 2: return launch_cfg<Cfg<5, 1>>(map_x, map_out, params, addend, HW, (int)tps, (int)total, inverse, grid, st);
+    default: return launch_cfg<Cfg<3, 2>>(map_x, map_out, params, addend, HW, (int)tps, (int)total, inverse, grid, st);
+  }
 }
 
 }  // namespace b200vc
