@@ -14,7 +14,7 @@ from b200vc import modules, ops  # noqa: E402
 from gpu_util import gc_case  # noqa: E402
 
 which = set(sys.argv[1:]) or {"gdn", "warp", "warp2", "blend", "gc", "eb"}
-reps = 3
+reps = int(os.environ.get("REPS", "1"))
 g = torch.Generator().manual_seed(0)
 N, H, W = 1, 1088, 1920
 
