@@ -16,9 +16,8 @@
 //     elementwise smem->smem copy with no index arithmetic.
 //   * D          = 128 lanes (channels) x 64 columns (positions) fp32 in TMEM; two accumulators per tile
 //     (D1 = ghi*hi, D2 = the small cross terms), double buffered: 256 + 2*128 = all 512 TMEM columns.
-//   * warp 0: TMA producer (ring of R raw tiles) | warp 1: TMEM alloc + MMA issuer (2 x 48 tcgen05.mma of N = 32
-//     per tile) | warps 2-9: square + hi/lo split (ring of A half-tile operand slots, so the split of one half
-//     overlaps the MMAs of the other) | warps 10-17: epilogue (tcgen05.ld ->
+//   * warp 0: TMA producer (ring of R raw tiles) | warp 1: TMEM alloc + MMA issuer (48 tcgen05.mma per tile) |
+//     warps 2-9: square + hi/lo split (ring of A operand pairs) | warps 10-17: epilogue (tcgen05.ld ->
 //     D1+D2+beta -> rsqrt/sqrt -> * x -> in place into the raw tile -> TMA store; the raw slot is released
 //     one tile later so the store drains behind the next tile's epilogue).
 // Algorithmic HBM traffic: 2*128*4 B per position (+128*4 with addend); 3 * 2*128*128 tensor flop per position.
@@ -43,14 +42,15 @@ constexpr uint32_t kTmemCols = 512;
 // TMEM columns: gamma hi | gamma lo | 2 accumulator stages x (D1: ghi*hi, D2: ghi*lo + glo*hi)
 constexpr uint32_t kColGhi = 0, kColGlo = 128, kColD = 256, kColDStage = 2 * kTileP;
 
-// Ring depths: R raw tiles of 64 positions (TMA load .. TMA store), A operand slots of HALF a tile each
-// (32 positions: hi 16 KB | lo 16 KB; square/split .. MMA done), so the split of half h+1 overlaps the MMAs of h.
+// Ring depths: R raw tiles (TMA load .. TMA store), A hi/lo operand pairs (square/split .. MMA done).
+// (A half-tile operand ring with N = 32 MMAs was measured SLOWER: a tcgen05.mma of N = 32 costs as much as
+// one of N = 64, so halving N doubles tensor time.)
 template <int R, int A>
 struct Cfg {
   static constexpr int kRaw = R, kAb = A;
   static constexpr int kRawOff = 0;
-  static constexpr int kAbOff = R * kTileBytes;              // A x (hi half | lo half)
-  static constexpr int kBarOff = kAbOff + A * 2 * kHalfBytes;
+  static constexpr int kAbOff = R * kTileBytes;              // A x (hi | lo)
+  static constexpr int kBarOff = kAbOff + A * 2 * kTileBytes;
   static constexpr int kNumBars = 2 * R + 2 * A + 4;
   static constexpr int kSmemBytes = kBarOff + 8 * kNumBars + 16 + 1024 /*alignment slack*/;
 };
@@ -112,15 +112,15 @@ __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bu
 __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)((kHalfBytes >> 4) & 0x3FFF) << 16;  // leading byte offset (unused: N = 32 is one atom)
+  d |= (uint64_t)((kHalfBytes >> 4) & 0x3FFF) << 16;  // leading byte offset  (16 KB between the two atoms)
   d |= (uint64_t)((512 >> 4) & 0x3FFF) << 32;         // stride byte offset   (4 rows x 128 B)
   d |= (uint64_t)1 << 46;                              // descriptor version (Blackwell)
   d |= (uint64_t)1 << 61;                              // SWIZZLE_128B_BASE32B
   return d;
 }
-// kind::tf32, D = F32, A = B = TF32, A K-major (TMEM), B MN-major, N = 32 (half a tile), M = 128.
+// kind::tf32, D = F32, A = B = TF32, A K-major (TMEM), B MN-major, N = 64, M = 128.
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (1u << 16) |
-                            ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(kC >> 4) << 24);
+                            ((uint32_t)(kTileP >> 3) << 17) | ((uint32_t)(kC >> 4) << 24);
 
 __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t accumulate) {
   asm volatile(
@@ -175,8 +175,8 @@ gdn_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   auto raw_addr = [&](int r) { return smem_base + CFG::kRawOff + r * kTileBytes; };
-  auto hi_addr = [&](int a) { return smem_base + CFG::kAbOff + a * 2 * kHalfBytes; };
-  auto lo_addr = [&](int a) { return smem_base + CFG::kAbOff + a * 2 * kHalfBytes + kHalfBytes; };
+  auto hi_addr = [&](int a) { return smem_base + CFG::kAbOff + a * 2 * kTileBytes; };
+  auto lo_addr = [&](int a) { return smem_base + CFG::kAbOff + a * 2 * kTileBytes + kTileBytes; };
   const uint32_t bar_base = smem_base + CFG::kBarOff;
   auto raw_full = [&](int r) { return bar_base + 8 * r; };
   auto raw_empty = [&](int r) { return bar_base + 8 * (R + r); };
@@ -258,63 +258,58 @@ gdn_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     if (lane == 0) {
       int k = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++k) {
-        const int d = k & 1, pd = (k >> 1) & 1;
+        const int a = k % A, pa = (k / A) & 1, d = k & 1, pd = (k >> 1) & 1;
         mbar_wait(d_empty(d), pd ^ 1);
-#pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-          const int hk = 2 * k + h, a = hk % A, pa = (hk / A) & 1;
-          mbar_wait(ab_full(a), pa);
-          tc_fence_after();
-          // Two accumulators: the tensor core's fp32 accumulation truncates, so the 32 small cross-term steps
-          // go to their own accumulator and never disturb the 16-step main sum; the epilogue adds them (RN).
-          const uint32_t d1 = tmem + kColD + kColDStage * d + 32 * h, d2 = d1 + kTileP;
+        mbar_wait(ab_full(a), pa);
+        tc_fence_after();
+        // Two accumulators: the tensor core's fp32 accumulation truncates, so the 32 small cross-term steps
+        // go to their own accumulator and never disturb the 16-step main sum; the epilogue adds them (RN).
+        const uint32_t d1 = tmem + kColD + kColDStage * d, d2 = d1 + kTileP;
 #pragma unroll
-          for (int g = 0; g < kC / 8; ++g)   // D1  = ghi * hi
-            umma_tf32_ts(d1, tmem + kColGhi + 8 * g, make_b_desc(hi_addr(a) + g * 1024), g != 0 ? 1u : 0u);
+        for (int g = 0; g < kC / 8; ++g)   // D1  = ghi * hi
+          umma_tf32_ts(d1, tmem + kColGhi + 8 * g, make_b_desc(hi_addr(a) + g * 1024), g != 0 ? 1u : 0u);
 #pragma unroll
-          for (int g = 0; g < kC / 8; ++g)   // D2  = ghi * lo
-            umma_tf32_ts(d2, tmem + kColGhi + 8 * g, make_b_desc(lo_addr(a) + g * 1024), g != 0 ? 1u : 0u);
+        for (int g = 0; g < kC / 8; ++g)   // D2  = ghi * lo
+          umma_tf32_ts(d2, tmem + kColGhi + 8 * g, make_b_desc(lo_addr(a) + g * 1024), g != 0 ? 1u : 0u);
 #pragma unroll
-          for (int g = 0; g < kC / 8; ++g)   // D2 += glo * hi
-            umma_tf32_ts(d2, tmem + kColGlo + 8 * g, make_b_desc(hi_addr(a) + g * 1024), 1u);
-          umma_commit(ab_empty(a));  // operand half consumed
-        }
-        umma_commit(d_full(d));      // both halves accumulated
+        for (int g = 0; g < kC / 8; ++g)   // D2 += glo * hi
+          umma_tf32_ts(d2, tmem + kColGlo + 8 * g, make_b_desc(hi_addr(a) + g * 1024), 1u);
+        umma_commit(ab_empty(a));  // operand pair consumed
+        umma_commit(d_full(d));    // accumulators ready
       }
     }
   } else if (warp < kFirstEpi) {
     // ------------------------------------------------------------------ square + TF32 hi/lo split (8 warps)
     const int t = threadIdx.x - kFirstXf * 32;
+    constexpr int kIters = kTileBytes / 16 / (kXfWarps * 32);  // 8 float4 per thread
     int k = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++k) {
-      const int r = k % R, pr = (k / R) & 1;
+      const int r = k % R, pr = (k / R) & 1, a = k % A, pa = (k / A) & 1;
       mbar_wait(raw_full(r), pr);
-#pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
-        const int hk = 2 * k + h, a = hk % A, pa = (hk / A) & 1;
-        mbar_wait(ab_empty(a), pa ^ 1);
-        const float4* raw4 =
-            reinterpret_cast<const float4*>(smem_gen + CFG::kRawOff + r * kTileBytes + h * kHalfBytes);
-        float4* hi4 = reinterpret_cast<float4*>(smem_gen + CFG::kAbOff + a * 2 * kHalfBytes);
-        float4* lo4 = hi4 + kHalfBytes / 16;
-        float4 v[kHalfBytes / 16 / (kXfWarps * 32)];
+      const float4* raw4 = reinterpret_cast<const float4*>(smem_gen + CFG::kRawOff + r * kTileBytes);
+      float4* hi4 = reinterpret_cast<float4*>(smem_gen + CFG::kAbOff + a * 2 * kTileBytes);
+      float4* lo4 = hi4 + kTileBytes / 16;
+      mbar_wait(ab_empty(a), pa ^ 1);
 #pragma unroll
-        for (int it = 0; it < kHalfBytes / 16 / (kXfWarps * 32); ++it) v[it] = raw4[it * (kXfWarps * 32) + t];
+      for (int b0 = 0; b0 < kIters; b0 += 4) {
+        float4 v[4];
 #pragma unroll
-        for (int it = 0; it < kHalfBytes / 16 / (kXfWarps * 32); ++it) {
+        for (int it = 0; it < 4; ++it) v[it] = raw4[(b0 + it) * (kXfWarps * 32) + t];  // 4 loads in flight
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
           float4 sq, hh, ll;
           sq.x = __fmul_rn(v[it].x, v[it].x); sq.y = __fmul_rn(v[it].y, v[it].y);
           sq.z = __fmul_rn(v[it].z, v[it].z); sq.w = __fmul_rn(v[it].w, v[it].w);
           hh.x = to_tf32_rna(sq.x); hh.y = to_tf32_rna(sq.y); hh.z = to_tf32_rna(sq.z); hh.w = to_tf32_rna(sq.w);
           ll.x = __fsub_rn(sq.x, hh.x); ll.y = __fsub_rn(sq.y, hh.y);
           ll.z = __fsub_rn(sq.z, hh.z); ll.w = __fsub_rn(sq.w, hh.w);
-          hi4[it * (kXfWarps * 32) + t] = hh;
-          lo4[it * (kXfWarps * 32) + t] = ll;
+          hi4[(b0 + it) * (kXfWarps * 32) + t] = hh;
+          lo4[(b0 + it) * (kXfWarps * 32) + t] = ll;
         }
-        fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
-        __syncwarp();
-        if (lane == 0) mbar_arrive(ab_full(a));
       }
+      fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ab_full(a));
     }
   } else {
     // ------------------------------------------------------------------ epilogue (8 warps)
@@ -341,30 +336,37 @@ gdn_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
       float4* raw4 = reinterpret_cast<float4*>(smem_gen + CFG::kRawOff + r * kTileBytes) + h * (kHalfBytes / 16) + i * 8;
       const float* arow = addend ? addend + ((int64_t)row0 + i) * HW + p0 + 32 * h : nullptr;
       const int64_t pbase = (int64_t)p0 + 32 * h;
+      // logical 16-byte chunk cc of row i lives at 32-byte chunk ((cc >> 1) ^ (i & 3)), same 16-byte half;
+      // lanes with `flip` take the odd chunk of each pair first => the 8 rows of a quarter-warp hit 8 distinct
+      // 16-byte bank groups (conflict-free LDS.128 / STS.128).  All loads are issued before any store.
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        // logical 16-byte chunk cc of row i lives at 32-byte chunk ((cc >> 1) ^ (i & 3)), same 16-byte half;
-        // lanes with `flip` take the odd chunk of each pair first => the 8 rows of a quarter-warp hit 8
-        // distinct 16-byte bank groups (conflict-free LDS.128 / STS.128)
-        const int cc = c ^ (int)flip;
-        float4* slot = raw4 + ((((cc >> 1) ^ (i & 3)) << 1) | (cc & 1));
-        const float4 x = *slot;
-        float o[4];
-        const float xe[4] = {x.x, x.y, x.z, x.w};
+      for (int c0 = 0; c0 < 8; c0 += 4) {
+        float4 xv[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const uint32_t u1 = flip ? v1[4 * (c ^ 1) + e] : v1[4 * c + e];
-          const uint32_t u2 = flip ? v2[4 * (c ^ 1) + e] : v2[4 * c + e];
-          const float acc = __fadd_rn(__uint_as_float(u1), __uint_as_float(u2));
-          const float nr = __fadd_rn(acc, beta);
-          o[e] = inverse == 2 ? nr : __fmul_rn(xe[e], inverse ? sqrtf(nr) : rsqrtf(nr));
+        for (int c = c0; c < c0 + 4; ++c) {
+          const int cc = c ^ (int)flip;
+          xv[c - c0] = raw4[(((cc >> 1) ^ (i & 3)) << 1) | (cc & 1)];
         }
-        if (arow != nullptr && pbase + 4 * cc < HW) {
-          const float4 a4 = *reinterpret_cast<const float4*>(arow + 4 * cc);
-          o[0] = __fadd_rn(o[0], a4.x); o[1] = __fadd_rn(o[1], a4.y);
-          o[2] = __fadd_rn(o[2], a4.z); o[3] = __fadd_rn(o[3], a4.w);
+#pragma unroll
+        for (int c = c0; c < c0 + 4; ++c) {
+          const int cc = c ^ (int)flip;
+          float o[4];
+          const float xe[4] = {xv[c - c0].x, xv[c - c0].y, xv[c - c0].z, xv[c - c0].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const uint32_t u1 = flip ? v1[4 * (c ^ 1) + e] : v1[4 * c + e];
+            const uint32_t u2 = flip ? v2[4 * (c ^ 1) + e] : v2[4 * c + e];
+            const float acc = __fadd_rn(__uint_as_float(u1), __uint_as_float(u2));
+            const float nr = __fadd_rn(acc, beta);
+            o[e] = inverse == 2 ? nr : __fmul_rn(xe[e], inverse ? sqrtf(nr) : rsqrtf(nr));
+          }
+          if (arow != nullptr && pbase + 4 * cc < HW) {
+            const float4 a4 = *reinterpret_cast<const float4*>(arow + 4 * cc);
+            o[0] = __fadd_rn(o[0], a4.x); o[1] = __fadd_rn(o[1], a4.y);
+            o[2] = __fadd_rn(o[2], a4.z); o[3] = __fadd_rn(o[3], a4.w);
+          }
+          raw4[(((cc >> 1) ^ (i & 3)) << 1) | (cc & 1)] = make_float4(o[0], o[1], o[2], o[3]);
         }
-        *slot = make_float4(o[0], o[1], o[2], o[3]);
       }
       fence_proxy_async();  // result tile (generic writes) -> visible to the TMA store
       asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -469,9 +471,9 @@ int launch_gdn_tc(const float* x, const float* params, const float* addend, floa
     return e ? atoi(e) : 0;
   }();
   switch (cfg) {
-    case 1: return launch_cfg<Cfg<4, 3>>(map_x, map_out, params, addend, HW, (int)tps, (int)total, inverse, grid, st);
-    case 2: return launch_cfg<Cfg<5, 2>>(map_x, map_out, params, addend, HW, (int)tps, (int)total, inverse, grid, st);
-    default: return launch_cfg<Cfg<4, 2>>(map_x, map_out, params, addend, HW, (int)tps, (int)total, inverse, grid, st);
+    case 1: return launch_cfg<Cfg<3, 2>>(map_x, map_out, params, addend, HW, (int)tps, (int)total, inverse, grid, st);
+    case 2: return launch_cfg<Cfg<5, 1>>(map_x, map_out, params, addend, HW, (int)tps, (int)total, inverse, grid, st);
+    default: return launch_cfg<Cfg<4, 1>>(map_x, map_out, params, addend, HW, (int)tps, (int)total, inverse, grid, st);
   }
 }
 
