@@ -471,9 +471,10 @@ int launch_gdn_tc(const float* x, const float* params, const float* addend, floa
     return e ? atoi(e) : 0;
   }();
   switch (cfg) {
+    // measured on B200 at [4,128,544,960]: <5,1> 4178 GB/s, <4,1> 4072 GB/s, <3,2> 3017 GB/s (raw-ring depth wins)
     case 1: return launch_cfg<Cfg<3, 2>>(map_x, map_out, params, addend, HW, (int)tps, (int)total, inverse, grid, st);
-    case 2: return launch_cfg<Cfg<5, 1>>(map_x, map_out, params, addend, HW, (int)tps, (int)total, inverse, grid, st);
-    default: return launch_cfg<Cfg<4, 1>>(map_x, map_out, params, addend, HW, (int)tps, (int)total, inverse, grid, st);
+    case 2: return launch_cfg<Cfg<4, 1>>(map_x, map_out, params, addend, HW, (int)tps, (int)total, inverse, grid, st);
+    default: return launch_cfg<Cfg<5, 1>>(map_x, map_out, params, addend, HW, (int)tps, (int)total, inverse, grid, st);
   }
 }
 
