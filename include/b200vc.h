@@ -120,7 +120,8 @@ B200VC_API int64_t b200vc_gdn_params_floats(int C);
 B200VC_API int b200vc_gdn_prepare_f32(const float* beta, const float* gamma, float beta_bound, float gamma_bound,
                            float pedestal, float* params_out, int C, void* stream);
 /*   x, out [N,C,HW]; addend (nullable) [N,C,HW] is added to the result (the residual-block skip,
- *   compressai ResidualBlockWithStride/ResidualBlockUpsample `out += identity`); out must not alias x or addend.
+ *   compressai ResidualBlockWithStride/ResidualBlockUpsample `out += identity`); out must not alias x; out == addend is allowed and
+ *   is the fast path (in-place residual add: the tensor-core kernel accumulates with a TMA reduce-add).
  *   out_i = x_i * rsqrt(beta_i + sum_j gamma_ij x_j^2)    (inverse == 1: * sqrt; inverse == 2, diagnostics:
  *   out_i = the norm beta_i + sum_j gamma_ij x_j^2 itself).
  *   impl: 0 = auto, 1 = CUDA-core fp32 kernel (any C % 32 == 0), 2 = tcgen05 3xTF32 kernel (C == 128).

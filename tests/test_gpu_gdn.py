@@ -54,8 +54,31 @@ def test_gdn_at_init_closed_form_and_addend(strict_fp32):
     with torch.no_grad():
         got = modules.gdn_forward(p, x)
         torch.testing.assert_close(got, x / torch.sqrt(1 + 0.1 * x ** 2), rtol=1e-5, atol=1e-7)
-        fused = modules.gdn_forward(p, x, addend=skip)
-        assert torch.equal(fused, got + skip)
+        want = got + skip
+        fused = modules.gdn_forward(p, x, addend=skip.clone())  # the addend tensor is consumed (in-place add)
+        assert torch.equal(fused, want)
+
+
+@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_gdn_residual_add_both_forms(strict_fp32, impl, inverse):
+    """out = gdn(x) + addend: separate output buffer vs in-place accumulation (TMA reduce-add on tcgen05)."""
+    from b200vc import _lib, modules, ops
+    o, p = _pair(128, inverse, trained_like=True)
+    x = _x(2, 128, 37, 52)
+    skip = torch.randn_like(x)
+    params = modules.gdn_params(p)
+    with torch.no_grad():
+        want = o(x) + skip
+    inplace = ops.gdn(x, params, inverse=inverse, addend=skip.clone(), impl=impl)
+    out = torch.empty_like(x)
+    rc = _lib.load().b200vc_gdn_f32(x.data_ptr(), params.data_ptr(), skip.data_ptr(), out.data_ptr(), 2, 128,
+                                    37 * 52, int(inverse), impl, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    for got in (inplace, out):
+        err = ((got - want).abs() / want.abs().clamp(min=1e-3)).max().item()
+        assert err < 1e-5, err
+    assert torch.equal(inplace, out)
 
 
 def test_gdn_params_track_weight_updates(strict_fp32):

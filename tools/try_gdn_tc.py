@@ -76,8 +76,8 @@ for (N, H, W) in [(1, 8, 8), (1, 5, 8), (1, 16, 20), (2, 33, 44), (1, 68, 120), 
         got = ops.gdn(x, params, inverse=inverse, impl=2)
         torch.cuda.synchronize()
         rel = ((got - ref).abs() / ref.abs().clamp(min=1e-6)).max().item()
-        got2 = ops.gdn(x, params, inverse=inverse, addend=skip, impl=2)
-        ref2 = ops.gdn(x, params, inverse=inverse, addend=skip, impl=1)
+        got2 = ops.gdn(x, params, inverse=inverse, addend=skip.clone(), impl=2)
+        ref2 = ops.gdn(x, params, inverse=inverse, addend=skip.clone(), impl=1)
         torch.cuda.synchronize()
         abs2 = (got2 - ref2).abs().max().item()
         print(f"N={N} {H}x{W} inverse={inverse}: max rel err vs fp32 kernel {rel:.3e}; with addend max abs {abs2:.3e}; "
@@ -87,18 +87,30 @@ flush_buf = torch.empty(256 * 1024 * 1024 // 4, device="cuda")
 print("B200VC_GDN_TC_CFG =", os.environ.get("B200VC_GDN_TC_CFG", "0"))
 for (N, H, W) in [(1, 544, 960), (4, 544, 960), (1, 272, 480), (1, 136, 240)]:
     x = torch.randn(N, C, H, W, device="cuda")
-    for impl in (1, 2):
-        ops.gdn(x, params, impl=impl)
+    skip = torch.randn(N, C, H, W, device="cuda")
+    out_sep = torch.empty_like(x)
+    from b200vc import _lib
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+
+    def sep():  # addend read from a separate tensor
+        lib.b200vc_gdn_f32(x.data_ptr(), params.data_ptr(), skip.data_ptr(), out_sep.data_ptr(), N, C, H * W, 0, 2, st)
+
+    cases = [("impl=1 plain", lambda: ops.gdn(x, params, impl=1), 2), ("impl=2 plain", lambda: ops.gdn(x, params, impl=2), 2),
+             ("impl=2 +addend in place (TMA reduce-add)", lambda: ops.gdn(x, params, addend=skip, impl=2), 3),
+             ("impl=2 +addend separate", sep, 3)]
+    for name, fn, words in cases:
+        fn()
         torch.cuda.synchronize()
         tot = 0.0
         for _ in range(10):
             flush_buf.add_(1.0)
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
-            ops.gdn(x, params, impl=impl)
+            fn()
             e.record()
             torch.cuda.synchronize()
             tot += s.elapsed_time(e)
         ms = tot / 10
-        gb = 1024 * N * H * W / ms / 1e6
-        print(f"impl={impl} N={N} {H}x{W}: {ms*1e3:.1f} us  {gb:.0f} GB/s  ({gb/6539.2:.1%} of measured peak)", flush=True)
+        gb = words * 512 * N * H * W / ms / 1e6
+        print(f"{name:42s} N={N} {H}x{W}: {ms*1e3:7.1f} us  {gb:5.0f} GB/s  ({gb/6539.2:.1%} of measured peak)", flush=True)

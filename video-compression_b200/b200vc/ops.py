@@ -247,10 +247,12 @@ def gdn_prepare(beta, gamma, beta_bound, gamma_bound, pedestal):
 
 
 _GDN_IMPL = int(os.environ.get("B200VC_GDN_IMPL", "0"))  # 0 auto (tcgen05 when C == 128), 1 exact fp32, 2 tcgen05
+_GDN_INPLACE_ADD = os.environ.get("B200VC_GDN_INPLACE_ADD", "1") != "0"
 
 
 def gdn(x, params, inverse=False, addend=None, impl=0):
-    """out = x * rsqrt(beta + gamma @ x^2) (IGDN: sqrt) [+ addend]; x is NCHW.
+    """out = x * rsqrt(beta + gamma @ x^2) (IGDN: sqrt) [+ addend]; x is NCHW.  With ``addend`` the sum is
+    written into the addend's own storage (it is consumed) and that tensor is returned.
     impl 0 = auto: the tcgen05 3xTF32 kernel for C == 128 (~1e-6 relative), else the exact-fp32 CUDA-core
     kernel; B200VC_GDN_IMPL=1 forces the exact kernel everywhere (bit-parity experiments)."""
     if impl == 0:
@@ -261,7 +263,9 @@ def gdn(x, params, inverse=False, addend=None, impl=0):
         addend = _contig(addend, "gdn(addend)")
         if addend.shape != x.shape:
             raise RuntimeError("gdn: addend shape mismatch")
-    out = torch.empty_like(x)
+    # residual form: accumulate into the addend's storage (the reference's `out += identity`); the tcgen05
+    # kernel then needs no addend traffic inside the SM -- the result tile leaves through a TMA reduce-add
+    out = addend if (addend is not None and _GDN_INPLACE_ADD) else torch.empty_like(x)
     lib = _lib.load()
     nbytes = (2 + (addend is not None)) * C * 4 * N * H * W
     _run("gdn_f32", nbytes, lambda: lib.b200vc_gdn_f32(

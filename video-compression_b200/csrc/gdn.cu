@@ -54,8 +54,8 @@ __global__ void gdn_prepare_kernel(const float* __restrict__ beta, const float* 
 // smem: gT[C][C] (gamma transposed, loaded once per persistent CTA) + xs[C][TP] (current x tile).
 template <int C, int TP>
 __global__ void __launch_bounds__(256, 1)
-gdn_fp32_kernel(const float* __restrict__ x, const float* __restrict__ params, const float* __restrict__ addend,
-                float* __restrict__ out, int64_t HW, int tiles_per_sample, int total_tiles, int inverse) {
+gdn_fp32_kernel(const float* __restrict__ x, const float* __restrict__ params, const float* addend,
+                float* out, int64_t HW, int tiles_per_sample, int total_tiles, int inverse) {
   constexpr int RG = C / 64;   // channel groups of 4 per thread
   constexpr int PG = TP / 64;  // position groups of 4 per thread
   extern __shared__ __align__(16) float smem[];
@@ -146,7 +146,7 @@ gdn_fp32_kernel(const float* __restrict__ x, const float* __restrict__ params, c
         if (vec_ok) {
           if (p < HW) {
             if (an) {
-              const float4 a4 = ld_stream4(an + (int64_t)i * HW + p);
+              const float4 a4 = *reinterpret_cast<const float4*>(an + (int64_t)i * HW + p);  // may alias `out`
               o[0] = __fadd_rn(o[0], a4.x); o[1] = __fadd_rn(o[1], a4.y);
               o[2] = __fadd_rn(o[2], a4.z); o[3] = __fadd_rn(o[3], a4.w);
             }

@@ -97,6 +97,16 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit_and_wait_read() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -168,8 +178,12 @@ __device__ __forceinline__ float to_tf32_rna(float v) {
 template <class CFG>
 __global__ void __launch_bounds__(kThreads, 1)
 gdn_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_out,
-              const float* __restrict__ params, const float* __restrict__ addend, int64_t HW,
-              int tiles_per_sample, int total_tiles, int inverse) {
+              const __grid_constant__ CUtensorMap map_add, const float* __restrict__ params,
+              const float* __restrict__ addend, int64_t HW, int tiles_per_sample, int total_tiles, int inverse,
+              int accumulate) {
+  // addend handling: accumulate != 0  => `out` already holds the addend (in-place residual add): the result
+  //                                      tile leaves through a TMA reduce-add, no addend traffic in the SM;
+  //                  addend != null   => the epilogue reads it from global (L2-prefetched by the producer).
   constexpr int R = CFG::kRaw, A = CFG::kAb;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -204,6 +218,7 @@ gdn_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_out)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_add)) : "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -251,6 +266,10 @@ gdn_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         mbar_arrive_expect_tx(raw_full(r), kTileBytes);
         tma_load_2d(raw_addr(r), &map_x, p0, row0, raw_full(r));
         tma_load_2d(raw_addr(r) + kHalfBytes, &map_x, p0 + 32, row0, raw_full(r));
+        if (addend != nullptr) {
+          tma_prefetch_l2_2d(&map_add, p0, row0);
+          if ((int64_t)p0 + 32 < HW) tma_prefetch_l2_2d(&map_add, p0 + 32, row0);
+        }
       }
     }
   } else if (warp == 1) {
@@ -341,11 +360,13 @@ gdn_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
       // 16-byte bank groups (conflict-free LDS.128 / STS.128).  All loads are issued before any store.
 #pragma unroll
       for (int c0 = 0; c0 < 8; c0 += 4) {
-        float4 xv[4];
+        float4 xv[4], av[4];
 #pragma unroll
         for (int c = c0; c < c0 + 4; ++c) {
           const int cc = c ^ (int)flip;
           xv[c - c0] = raw4[(((cc >> 1) ^ (i & 3)) << 1) | (cc & 1)];
+          av[c - c0] = (arow != nullptr && pbase + 4 * cc < HW) ? *reinterpret_cast<const float4*>(arow + 4 * cc)
+                                                                : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int c = c0; c < c0 + 4; ++c) {
@@ -360,8 +381,8 @@ gdn_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
             const float nr = __fadd_rn(acc, beta);
             o[e] = inverse == 2 ? nr : __fmul_rn(xe[e], inverse ? sqrtf(nr) : rsqrtf(nr));
           }
-          if (arow != nullptr && pbase + 4 * cc < HW) {
-            const float4 a4 = *reinterpret_cast<const float4*>(arow + 4 * cc);
+          if (arow != nullptr) {
+            const float4 a4 = av[c - c0];
             o[0] = __fadd_rn(o[0], a4.x); o[1] = __fadd_rn(o[1], a4.y);
             o[2] = __fadd_rn(o[2], a4.z); o[3] = __fadd_rn(o[3], a4.w);
           }
@@ -371,8 +392,13 @@ gdn_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
       fence_proxy_async();  // result tile (generic writes) -> visible to the TMA store
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (leader) {
-        tma_store_2d(&map_out, raw_addr(r), p0, row0);
-        if ((int64_t)p0 + 32 < HW) tma_store_2d(&map_out, raw_addr(r) + kHalfBytes, p0 + 32, row0);
+        if (accumulate) {
+          tma_reduce_add_2d(&map_out, raw_addr(r), p0, row0);
+          if ((int64_t)p0 + 32 < HW) tma_reduce_add_2d(&map_out, raw_addr(r) + kHalfBytes, p0 + 32, row0);
+        } else {
+          tma_store_2d(&map_out, raw_addr(r), p0, row0);
+          if ((int64_t)p0 + 32 < HW) tma_store_2d(&map_out, raw_addr(r) + kHalfBytes, p0 + 32, row0);
+        }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         // release the PREVIOUS tile's raw slot once its store has finished reading shared memory; the store
         // just issued keeps draining while the next tile's epilogue runs
@@ -427,8 +453,9 @@ static bool make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t 
 }
 
 template <class CFG>
-static int launch_cfg(const CUtensorMap& map_x, const CUtensorMap& map_out, const float* params, const float* addend,
-                      int64_t HW, int tps, int total, int inverse, int grid, cudaStream_t st) {
+static int launch_cfg(const CUtensorMap& map_x, const CUtensorMap& map_out, const CUtensorMap& map_add,
+                      const float* params, const float* addend, int64_t HW, int tps, int total, int inverse,
+                      int accumulate, int grid, cudaStream_t st) {
   static bool configured[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -441,7 +468,8 @@ static int launch_cfg(const CUtensorMap& map_x, const CUtensorMap& map_out, cons
     }
     configured[dev] = true;
   }
-  gdn_tc_kernel<CFG><<<grid, kThreads, CFG::kSmemBytes, st>>>(map_x, map_out, params, addend, HW, tps, total, inverse);
+  gdn_tc_kernel<CFG><<<grid, kThreads, CFG::kSmemBytes, st>>>(map_x, map_out, map_add, params, addend, HW, tps, total,
+                                                              inverse, accumulate);
   return check_launch("gdn_f32(tcgen05)");
 }
 
@@ -454,8 +482,12 @@ int launch_gdn_tc(const float* x, const float* params, const float* addend, floa
     set_error("gdn_f32: tcgen05 kernel needs C == 128 and HW %% 4 == 0 (got C=%d, HW=%lld)", C, (long long)HW);
     return B200VC_EUNSUPPORTED;
   }
-  CUtensorMap map_x, map_out;
-  if (!make_map(&map_x, x, (int64_t)N * C, HW) || !make_map(&map_out, out, (int64_t)N * C, HW)) {
+  // in-place residual add: `out` already holds the addend => accumulate through a TMA reduce-add
+  const int accumulate = (addend != nullptr && addend == out) ? 1 : 0;
+  if (accumulate) addend = nullptr;
+  CUtensorMap map_x, map_out, map_add;
+  if (!make_map(&map_x, x, (int64_t)N * C, HW) || !make_map(&map_out, out, (int64_t)N * C, HW) ||
+      !make_map(&map_add, addend ? addend : x, (int64_t)N * C, HW)) {
     set_error("gdn_f32: cuTensorMapEncodeTiled failed");
     return B200VC_EUNSUPPORTED;
   }
@@ -472,9 +504,12 @@ int launch_gdn_tc(const float* x, const float* params, const float* addend, floa
   }();
   switch (cfg) {
     // measured on B200 at [4,128,544,960]: <5,1> 4178 GB/s, <4,1> 4072 GB/s, <3,2> 3017 GB/s (raw-ring depth wins)
-    case 1: return launch_cfg<Cfg<3, 2>>(map_x, map_out, params, addend, HW, (int)tps, (int)total, inverse, grid, st);
-    case 2: return launch_cfg<Cfg<4, 1>>(map_x, map_out, params, addend, HW, (int)tps, (int)total, inverse, grid, st);
-    default: return launch_cfg<Cfg<5, 1>>(map_x, map_out, params, addend, HW, (int)tps, (int)total, inverse, grid, st);
+    case 1: return launch_cfg<Cfg<3, 2>>(map_x, map_out, map_add, params, addend, HW, (int)tps, (int)total, inverse,
+                                          accumulate, grid, st);
+    case 2: return launch_cfg<Cfg<4, 1>>(map_x, map_out, map_add, params, addend, HW, (int)tps, (int)total, inverse,
+                                          accumulate, grid, st);
+    default: return launch_cfg<Cfg<5, 1>>(map_x, map_out, map_add, params, addend, HW, (int)tps, (int)total, inverse,
+                                          accumulate, grid, st);
   }
 }
 
