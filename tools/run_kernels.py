@@ -31,7 +31,7 @@ if "gdn" in which:
     skip = torch.randn_like(x)
     for _ in range(reps):
         ops.gdn(x, params)
-        ops.gdn(x, params, inverse=True, addend=skip)
+        ops.gdn(x, params, inverse=True, addend=skip)  # in-place residual form (TMA reduce-add)
 if "warp" in which:
     img = torch.rand(N, 3, H, W, generator=g).cuda()
     flow = smooth_flow(N)
