@@ -324,7 +324,8 @@ def run_product(args):
         if dom:
             d = kernels[dom]
             roofline = {"bound": "hbm", "kernel": dom, "achieved": d["GBps"], "peak": peak, "unit": "GB/s",
-                        "frac": d["frac_of_peak"], "traffic": load_traffic(dom), "peak_source": peak_src,
+                        "frac": d["frac_of_peak"], "traffic": load_traffic(dom), "traffic_note": load_traffic_note(dom),
+                        "peak_source": peak_src,
                         "launches_per_step": d["launches"] / steps,
                         "hot_path_ms_per_step": hot_ms, "hot_path_GBps": hot_bytes / (hot_ms / 1e3) / 1e9 if hot_ms else None,
                         "hot_path_share_of_step": hot_ms / (ms_total / steps)}
@@ -363,10 +364,22 @@ def run_product(args):
 
 
 def load_traffic(kernel):
-    """DRAM bytes per launch from the committed ncu capture (profiles/traffic.json), or None."""
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the kernel from the committed
+    `ncu --set full` capture (profiles/traffic.json, profiles/r01_ncu_summary.md), or None."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f).get(kernel)
+            entry = json.load(f).get(kernel)
+        return entry["bytes_per_launch"] if entry else None
+    except Exception:
+        return None
+
+
+def load_traffic_note(kernel):
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            e = json.load(f).get(kernel)
+        return (f"ncu capture at {e['shape']}: {e['bytes_per_launch'] / 1e6:.1f} MB DRAM vs "
+                f"{e['algorithmic_bytes_per_launch'] / 1e6:.1f} MB algorithmic per launch") if e else None
     except Exception:
         return None
 
