@@ -14,6 +14,8 @@
 //
 // The coordinate path reproduces ATen's CUDA arithmetic operation by operation:
 // every step is pinned with __f*_rn intrinsics so nvcc cannot re-associate or contract differently.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b200vc {
@@ -131,39 +133,61 @@ __device__ __forceinline__ void coords(const WarpGeom& g, int x, int y, float u,
 }
 
 // CT > 0: channel count known at compile time (planes unrolled, all gathers of a pixel in flight together).
-template <int CT, int VARIANT, bool ARITH0>
+// PX: output pixels per thread (rows y, y+8, ...): the kernel is latency-bound (two dependent DRAM round trips per
+// pixel: flow, then taps), so each thread keeps PX independent chains in flight.
+template <int CT, int VARIANT, bool ARITH0, int PX>
 __global__ void __launch_bounds__(kWarpThreads)
 warp_kernel(const float* __restrict__ img, int64_t img_bs, const float* __restrict__ flow,
             const float* __restrict__ tab_x, const float* __restrict__ tab_y, float* __restrict__ out,
             int64_t out_bs, int C, WarpGeom g) {
   constexpr bool BORDER = (VARIANT != B200VC_WARP_FLEX);
+  constexpr int kRows = kWarpThreads / 32;
   const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int y = blockIdx.y * (kWarpThreads / 32) + (threadIdx.x >> 5);
+  const int y0 = blockIdx.y * (kRows * PX) + (threadIdx.x >> 5);
   const int n = blockIdx.z;
-  if (x >= g.W || y >= g.H) return;
+  if (x >= g.W) return;
   const int HW = g.H * g.W;
-  const int o = y * g.W + x;
-  const float* fu = flow + (int64_t)n * 2 * HW + o;
-  const float u = __ldg(fu), v = __ldg(fu + HW);
-  float tx = 0.f, ty = 0.f;
-  if (BORDER) {
-    tx = __ldg(tab_x + x);
-    ty = __ldg(tab_y + y);
+  const float* fbase = flow + (int64_t)n * 2 * HW;
+  float u[PX], v[PX];
+#pragma unroll
+  for (int k = 0; k < PX; ++k) {
+    const int y = y0 + k * kRows;
+    const int o = min(y, g.H - 1) * g.W + x;
+    u[k] = __ldg(fbase + o);
+    v[k] = __ldg(fbase + HW + o);
   }
-  float ix, iy;
-  coords<VARIANT, ARITH0>(g, x, y, u, v, tx, ty, ix, iy);
-  const Taps t = make_taps<BORDER>(ix, iy, g.H, g.W);
+  const float tx = BORDER ? __ldg(tab_x + x) : 0.f;
+  Taps t[PX];
+#pragma unroll
+  for (int k = 0; k < PX; ++k) {
+    const int y = min(y0 + k * kRows, g.H - 1);
+    const float ty = BORDER ? __ldg(tab_y + y) : 0.f;
+    float ix, iy;
+    coords<VARIANT, ARITH0>(g, x, y, u[k], v[k], tx, ty, ix, iy);
+    t[k] = make_taps<BORDER>(ix, iy, g.H, g.W);
+  }
   const float* ip = img + (int64_t)n * img_bs;
-  float* op = out + (int64_t)n * out_bs + o;
+  float* op = out + (int64_t)n * out_bs;
   if (CT > 0) {
-    float r[CT > 0 ? CT : 1];
+    float r[PX][CT > 0 ? CT : 1];
 #pragma unroll
-    for (int c = 0; c < CT; ++c) r[c] = sample<BORDER>(ip + (int64_t)c * HW, t);
+    for (int k = 0; k < PX; ++k)
 #pragma unroll
-    for (int c = 0; c < CT; ++c) op[(int64_t)c * HW] = r[c];
+      for (int c = 0; c < CT; ++c) r[k][c] = sample<BORDER>(ip + (int64_t)c * HW, t[k]);
+#pragma unroll
+    for (int k = 0; k < PX; ++k) {
+      const int y = y0 + k * kRows;
+      if (y < g.H) {
+#pragma unroll
+        for (int c = 0; c < CT; ++c) op[(int64_t)c * HW + y * g.W + x] = r[k][c];
+      }
+    }
   } else {
+    const int y = y0;  // PX == 1 in the generic-C instantiation
+    if (y < g.H) {
 #pragma unroll 4
-    for (int c = 0; c < C; ++c) op[(int64_t)c * HW] = sample<BORDER>(ip + (int64_t)c * HW, t);
+      for (int c = 0; c < C; ++c) op[(int64_t)c * HW + y * g.W + x] = sample<BORDER>(ip + (int64_t)c * HW, t[0]);
+    }
   }
 }
 
@@ -294,27 +318,44 @@ extern "C" int b200vc_warp_f32(const float* img, int64_t img_bs, const float* fl
   const int rows = kWarpThreads / 32;
   dim3 grid((W + 31) / 32, (H + rows - 1) / rows, N);
 #define B200VC_WARP_ARGS img, img_bs, flow, tab_x, tab_y, out, out_bs, C, g
+  static const int px_env = []() {
+    const char* e = getenv("B200VC_WARP_PX");
+    return e ? atoi(e) : 0;
+  }();
+  // pixels per thread: 2 when the plane is large enough to still fill the machine (tuned on B200)
+  const int px = (C > 4 || arith != 0) ? 1 : (px_env > 0 ? px_env : ((int64_t)N * H * W >= (1 << 19) ? 2 : 1));
+  const int rows_per_cta = rows * px;
+  grid = dim3((W + 31) / 32, (H + rows_per_cta - 1) / rows_per_cta, N);
+#define B200VC_WARP_LAUNCH_PX(CT, PX)                                                                      \
+  do {                                                                                                    \
+    if (variant == B200VC_WARP_LHBDC)                                                                     \
+      warp_kernel<CT, 0, true, PX><<<grid, kWarpThreads, 0, st>>>(B200VC_WARP_ARGS);                      \
+    else if (variant == B200VC_WARP_FLEX)                                                                 \
+      warp_kernel<CT, 1, true, PX><<<grid, kWarpThreads, 0, st>>>(B200VC_WARP_ARGS);                      \
+    else                                                                                                  \
+      warp_kernel<CT, 2, true, PX><<<grid, kWarpThreads, 0, st>>>(B200VC_WARP_ARGS);                      \
+  } while (0)
 #define B200VC_WARP_LAUNCH(CT)                                                                            \
   do {                                                                                                    \
-    if (arith != 0) {                                                                                     \
-      if (variant == B200VC_WARP_LHBDC) warp_kernel<0, 0, false><<<grid, kWarpThreads, 0, st>>>(B200VC_WARP_ARGS); \
-      else if (variant == B200VC_WARP_FLEX) warp_kernel<0, 1, false><<<grid, kWarpThreads, 0, st>>>(B200VC_WARP_ARGS); \
-      else warp_kernel<0, 2, false><<<grid, kWarpThreads, 0, st>>>(B200VC_WARP_ARGS);                     \
-    } else if (variant == B200VC_WARP_LHBDC)                                                              \
-      warp_kernel<CT, 0, true><<<grid, kWarpThreads, 0, st>>>(B200VC_WARP_ARGS);                          \
-    else if (variant == B200VC_WARP_FLEX)                                                                 \
-      warp_kernel<CT, 1, true><<<grid, kWarpThreads, 0, st>>>(B200VC_WARP_ARGS);                          \
-    else                                                                                                  \
-      warp_kernel<CT, 2, true><<<grid, kWarpThreads, 0, st>>>(B200VC_WARP_ARGS);                          \
+    if (px >= 4) B200VC_WARP_LAUNCH_PX(CT, 4);                                                            \
+    else if (px == 2) B200VC_WARP_LAUNCH_PX(CT, 2);                                                       \
+    else B200VC_WARP_LAUNCH_PX(CT, 1);                                                                    \
   } while (0)
-  switch (C) {
-    case 1: B200VC_WARP_LAUNCH(1); break;
-    case 2: B200VC_WARP_LAUNCH(2); break;
-    case 3: B200VC_WARP_LAUNCH(3); break;
-    case 4: B200VC_WARP_LAUNCH(4); break;
-    default: B200VC_WARP_LAUNCH(0); break;
+  if (arith != 0) {
+    if (variant == B200VC_WARP_LHBDC) warp_kernel<0, 0, false, 1><<<grid, kWarpThreads, 0, st>>>(B200VC_WARP_ARGS);
+    else if (variant == B200VC_WARP_FLEX) warp_kernel<0, 1, false, 1><<<grid, kWarpThreads, 0, st>>>(B200VC_WARP_ARGS);
+    else warp_kernel<0, 2, false, 1><<<grid, kWarpThreads, 0, st>>>(B200VC_WARP_ARGS);
+  } else {
+    switch (C) {
+      case 1: B200VC_WARP_LAUNCH(1); break;
+      case 2: B200VC_WARP_LAUNCH(2); break;
+      case 3: B200VC_WARP_LAUNCH(3); break;
+      case 4: B200VC_WARP_LAUNCH(4); break;
+      default: B200VC_WARP_LAUNCH_PX(0, 1); break;
+    }
   }
 #undef B200VC_WARP_LAUNCH
+#undef B200VC_WARP_LAUNCH_PX
 #undef B200VC_WARP_ARGS
   return check_launch("warp_f32");
 }
