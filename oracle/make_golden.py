@@ -132,6 +132,33 @@ def main():
     np.savez_compressed(os.path.join(OUT, "lhbdc_model_reference.npz"), **out)
     print("lhbdc_model_reference.npz written")
 
+    # ---- Flex-Rate BidirFlowRef through the compressai stand-in --------------------------------------
+    from oracle import flexrate as o_flex
+    ref_b = shim.import_reference(os.path.join(REF, "Flex-Rate-Hier-Bidir-Video-Compression"), "b_model.b_model")
+
+    def build_flex(cls):
+        torch.manual_seed(0)
+        m = cls(n=4, N=128).eval()
+        synthetic.calibrate_flex_(m, 0)
+        return m
+
+    rf, of = build_flex(ref_b.BidirFlowRef), build_flex(o_flex.BidirFlowRef)
+    sd_r, sd_o = rf.state_dict(), of.state_dict()
+    assert set(sd_r) == set(sd_o) and all(torch.equal(sd_r[k], sd_o[k]) for k in sd_r)
+    tri = seq[[0, 4, 8]][:, :, :128, :192]
+    xb, xc, xa = (tri[i:i + 1].float() / 255.0 for i in range(3))
+    fout = {"frames_u8": tri.numpy()}
+    with torch.no_grad():
+        for tag, (n, l) in {"n1_l1": ([1], 1.0), "n0_l066": ([0], 0.66)}.items():
+            r = rf(xb, xc, xa, n=n, l=l, train=False)
+            o = of(xb, xc, xa, n=n, l=l, train=False)
+            assert torch.equal(r["x_hat"], o["x_hat"]) and torch.equal(r["size"], o["size"])
+            fout.update({f"{tag}_x_hat": r["x_hat"].numpy(), f"{tag}_size": r["size"].numpy(),
+                         f"{tag}_rate": r["rate"].numpy()})
+            print("flex", tag, "size", r["size"].tolist())
+    np.savez_compressed(os.path.join(OUT, "flexrate_model_reference.npz"), **fout)
+    print("flexrate_model_reference.npz written")
+
 
 if __name__ == "__main__":
     main()

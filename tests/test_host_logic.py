@@ -94,3 +94,25 @@ def test_psnr_from_sse():
     sse = torch.tensor(3.0 * 10 * 10 * 4.0, dtype=torch.float64)  # every value off by 2
     import math
     assert abs(gop.psnr_from_sse(sse, 300).item() - 10 * math.log10(255.0 ** 2 / 4)) < 1e-9
+
+
+def test_flexrate_mirror_checkpoint_layout_and_gains():
+    from b200vc import flexrate
+    from oracle import flexrate as o_flex
+    torch.manual_seed(0)
+    orc = o_flex.BidirFlowRef(n=4, N=128)
+    prod = flexrate.BidirFlowRef(n=4, N=128)
+    a, b = prod.state_dict(), orc.state_dict()
+    assert set(a) == set(b) and all(a[k].shape == b[k].shape for k in a)
+    prod.load_state_dict(b, strict=True)
+    for k in ("flow_compressor.gain_unit.gain_matrix", "residual_compressor.hyper_inv_gain_unit.gain_matrix",
+              "flow_predictor.down_path.4.block.2.weight", "Mask.up_path.2.up.1.bias", "flow_compressor.g_s.7.0.weight"):
+        assert k in a, k
+    assert a["flow_compressor.g_s.7.0.weight"].shape[0] == 4 * 4 and a["flow_compressor.g_a.0.conv1.weight"].shape[1] == 19
+    synthetic.calibrate_flex_(orc, 0)
+    prod.load_state_dict(orc.state_dict())
+    gp, go = prod.flow_compressor.gain_unit, orc.flow_compressor.gain_unit
+    for n, l in (([1], 1.0), ([0], 0.33), ([2], 0.66)):
+        assert torch.equal(gp.gain(n, l), go.gain(n, l)) and gp.gain(n, l).shape == (1, 128)
+    with pytest.raises(NotImplementedError):
+        prod.flow_compressor.compress(torch.rand(1, 19, 64, 64), [0], 1.0)

@@ -86,3 +86,22 @@ def test_synthetic_sequence_is_deterministic(model_golden):
     want = torch.from_numpy(model_golden["synthetic_u8"])
     diff = (seq[[0, 4, 8]].int() - want.int()).abs()
     assert diff.max().item() <= 1 and (diff > 0).float().mean().item() < 1e-3
+
+
+@pytest.mark.parametrize("tag,n,l", [("n1_l1", [1], 1.0), ("n0_l066", [0], 0.66)])
+def test_flexrate_restatement_matches_reference(golden_dir, tag, n, l):
+    """Golden = the reference's own b_model/b_model.py BidirFlowRef (imported through the compressai stand-in)."""
+    from b200vc import synthetic
+    from oracle import flexrate as o_flex
+    gold = np.load(os.path.join(golden_dir, "flexrate_model_reference.npz"))
+    torch.manual_seed(0)
+    m = o_flex.BidirFlowRef(n=4, N=128).eval()
+    synthetic.calibrate_flex_(m, 0)
+    tri = torch.from_numpy(gold["frames_u8"])
+    xb, xc, xa = (tri[i:i + 1].float() / 255.0 for i in range(3))
+    with torch.no_grad():
+        out = m(xb, xc, xa, n=n, l=l, train=False)
+    want = torch.from_numpy(gold[f"{tag}_x_hat"])
+    assert ((out["x_hat"] - want).abs() < 1e-3).float().mean().item() > 0.999
+    assert abs(out["size"].item() - float(gold[f"{tag}_size"][0])) / float(gold[f"{tag}_size"][0]) < 1e-3
+    assert out["rate"].shape == (1,) and abs(out["rate"].item() - out["size"].item() / (128 * 192)) < 1e-3

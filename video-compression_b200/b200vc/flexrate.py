@@ -1,0 +1,195 @@
+"""Host-side mirror of the Flex-Rate hierarchical bidirectional codec interface (reference:
+``Flex-Rate-Hier-Bidir-Video-Compression/b_model/b_model.py`` ``BidirFlowRef``, ``b_model/layers.py``
+``Gain_Module`` / ``FlowCompressor`` / ``ResidualCompressor``, ``b_model/unet.py`` ``UNet``).  Same names, call
+signatures (``forward(x_before, x_current, x_after, n=[int], l=float, train=False) -> {"x_hat","size","rate"}``) and
+state-dict keys; the hot path runs in the sm_100a kernels:
+
+* ``backwarp`` x4 -> K-WARP, FLEX variant (zeros padding, half-pixel grid: b_model.py:99-112)
+* sigmoid + normalised blend + residual (b_model.py:68-73) -> K-BLEND, NORMW form (one pass)
+* every GDN / IGDN (+ residual add) -> K-GDN
+* ``hyper_gain_unit`` -> EntropyBottleneck -> ``hyper_inv_gain_unit`` (layers.py:140-143) -> K-EB with gain prologue and
+  inverse-gain epilogue; GaussianConditional -> ``inv_gain_unit`` (layers.py:145-146) -> K-GC with inverse-gain epilogue
+* per-sample bit sums (b_model.py:80-90) -> fp64 partials inside the two entropy kernels
+
+U-Nets and conv stacks stay on cuDNN (out of scope).
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import modules as M
+from . import ops
+from .lhbdc import _Compressor
+
+
+class UNetConvBlock(nn.Module):
+    def __init__(self, in_size, out_size, padding):
+        super().__init__()
+        pad = int(padding)
+        self.block = nn.Sequential(nn.Conv2d(in_size, out_size, kernel_size=3, padding=pad), nn.LeakyReLU(0.1),
+                                   nn.Conv2d(out_size, out_size, kernel_size=3, padding=pad), nn.LeakyReLU(0.1))
+
+    def forward(self, x):
+        return self.block(x)
+
+
+class UNetUpBlock(nn.Module):
+    def __init__(self, in_size, out_size, padding):
+        super().__init__()
+        self.up = nn.Sequential(nn.Upsample(mode="bilinear", scale_factor=2),
+                                nn.Conv2d(in_size, out_size, kernel_size=3, padding=1))
+        self.conv_block = UNetConvBlock(in_size, out_size, padding)
+
+    def forward(self, x, bridge):
+        up = self.up(x)
+        th, tw = up.shape[2:]
+        dy, dx = (bridge.shape[2] - th) // 2, (bridge.shape[3] - tw) // 2
+        return self.conv_block(torch.cat((up, bridge[:, :, dy:dy + th, dx:dx + tw]), 1))
+
+
+class UNet(nn.Module):
+    """b_model/unet.py (tunable U-Net): depth x [conv3-lrelu-conv3-lrelu], avg-pool down, bilinear up."""
+
+    def __init__(self, in_channels=1, n_classes=2, depth=5, wf=5, padding=True):
+        super().__init__()
+        self.padding, self.depth = padding, depth
+        widths = [2 ** (wf + i) for i in range(depth)]
+        self.down_path = nn.ModuleList(
+            UNetConvBlock(i, o, padding) for i, o in zip([in_channels] + widths[:-1], widths))
+        self.midconv = nn.Conv2d(widths[-1], widths[-1], kernel_size=3, padding=1)
+        self.up_path = nn.ModuleList(
+            UNetUpBlock(widths[i + 1], widths[i], padding) for i in reversed(range(depth - 1)))
+        self.last = nn.Conv2d(widths[0], n_classes, kernel_size=3, padding=1)
+
+    def forward(self, x):
+        skips = []
+        for i, down in enumerate(self.down_path):
+            x = down(x)
+            if i + 1 < len(self.down_path):
+                skips.append(x)
+                x = F.avg_pool2d(x, 2)
+        x = F.leaky_relu(self.midconv(x), negative_slope=0.1)
+        for up, skip in zip(self.up_path, reversed(skips)):
+            x = up(x, skip)
+        return self.last(x)
+
+
+class Gain_Module(nn.Module):
+    """layers.py:40-73.  ``gain(n, l)`` is the per-channel vector; the multiply itself is fused into the entropy
+    kernels wherever the scaled tensor is not needed by a convolution."""
+
+    def __init__(self, n=6, N=128, bias=False, inv=False):
+        super().__init__()
+        self.gain_matrix = nn.Parameter(torch.ones(n, N))
+        if bias:
+            raise NotImplementedError("the reference instantiates Gain_Module with bias=False only")
+        self.bias = False
+
+    def gain(self, n, l):
+        if l != 1:
+            return (torch.abs(self.gain_matrix[n]) ** l) * (torch.abs(self.gain_matrix[[n[0] + 1]]) ** (1 - l))
+        return torch.abs(self.gain_matrix[n])
+
+    def forward(self, x, n=None, l=1):
+        return self.gain(n, l).unsqueeze(2).unsqueeze(3) * x
+
+
+class _GainedCompressor(_Compressor):
+    def __init__(self, n, in_ch, out_ch, N):
+        super().__init__(in_ch, N)
+        if out_ch != in_ch:
+            self.g_s[-1] = M.subpel_conv3x3(N, out_ch, 2)
+        self.gain_unit = Gain_Module(n=n, N=N)
+        self.inv_gain_unit = Gain_Module(n=n, N=N, inv=True)
+        self.hyper_gain_unit = Gain_Module(n=n, N=N)
+        self.hyper_inv_gain_unit = Gain_Module(n=n, N=N, inv=True)
+
+    def _stages(self, x, n, l, want_lik):
+        eb, gc = self.entropy_bottleneck, self.gaussian_conditional
+        y = self.g_a(x)
+        scaled_y = self.gain_unit(y, n, l)          # needed dense by h_a (a convolution)
+        z = self.h_a(scaled_y)
+        rz = ops.entropy_bottleneck(z, M.eb_packed(eb), lik_bound=M._lik_bound(eb),
+                                    gain=self.hyper_gain_unit.gain(n, l), inv_gain=self.hyper_inv_gain_unit.gain(n, l),
+                                    want_lik=want_lik)
+        scales_hat, means_hat = self.h_s(rz["z_hat"]).chunk(2, 1)
+        ry = ops.gauss_cond(scaled_y, scales_hat, means_hat, scale_bound=M._scale_bound(gc),
+                            lik_bound=M._lik_bound(gc), inv_gain=self.inv_gain_unit.gain(n, l), want_lik=want_lik)
+        return self.g_s(ry["y_hat"]), ry, rz
+
+    def forward(self, x, n=None, l=None, train=False):
+        """layers.py:135-152 -- API-compatible dict with materialised likelihoods."""
+        if train:
+            raise NotImplementedError("b200vc mirrors the inference path (train=False) only")
+        x_hat, ry, rz = self._stages(x, n, l, want_lik=True)
+        return {"x_hat": x_hat, "likelihoods": {"y": ry["lik"], "z": rz["lik"]}}
+
+    def forward_bits(self, x, n, l):
+        x_hat, ry, rz = self._stages(x, n, l, want_lik=False)
+        return x_hat, ry["bits"], rz["bits"]
+
+    def compress(self, x, n, l):
+        raise NotImplementedError("rANS bitstream production is the 'next' row of SURVEY.md 8f")
+
+    decompress = compress
+
+
+class FlowCompressor(_GainedCompressor):
+    def __init__(self, n=6, in_ch=19, out_ch=5, N=128, bias=False, **kwargs):
+        super().__init__(n, in_ch, out_ch, N)
+        self.g_s[-1][0].weight.data.fill_(0.0)  # layers.py:125-126
+        self.g_s[-1][0].bias.data.fill_(0.0)
+
+
+class ResidualCompressor(_GainedCompressor):
+    def __init__(self, n=6, in_ch=3, N=128, bias=False, **kwargs):
+        super().__init__(n, in_ch, in_ch, N)
+
+
+class BidirFlowRef(nn.Module):
+    """Bidirectional compression with flow refinement (b_model.py:21-112)."""
+
+    def __init__(self, n=6, N=128):
+        super().__init__()
+        self.flow_predictor = UNet(6, 4, 5)
+        self.Mask = UNet(16, 2, 4)
+        self.flow_compressor = FlowCompressor(n=n, in_ch=19, out_ch=4, N=N, bias=False)
+        self.residual_compressor = ResidualCompressor(n=n, in_ch=3, N=N, bias=False)
+
+    def backwarp(self, img, flow):
+        return ops.backwarp(img, flow, "flex")
+
+    def process(self, x0, x1, t=0.5):
+        N, _, H, W = x0.shape
+        flow = self.flow_predictor(torch.cat((x0, x1), 1))
+        f01, f10 = flow[:, :2], flow[:, 2:4]
+        ft0 = -(1 - t) * t * f01 + t * t * f10
+        ft1 = (1 - t) * (1 - t) * f01 - t * (1 - t) * f10
+        conc = torch.empty((N, 16, H, W), device=x0.device, dtype=x0.dtype)  # cat(ft0, ft1, x0, x1, xt1, xt2)
+        conc[:, 0:2], conc[:, 2:4], conc[:, 4:7], conc[:, 7:10] = ft0, ft1, x0, x1
+        ops.backwarp(x0, ft0, "flex", out=conc[:, 10:13])
+        ops.backwarp(x1, ft1, "flex", out=conc[:, 13:16])
+        return ft0, ft1, conc
+
+    def forward_device(self, x_before, x_current, x_after, n, l):
+        N, _, H, W = x_current.shape
+        mv_before, mv_after, x_conc = self.process(x_before, x_after)
+        flow_hat, fy, fz = self.flow_compressor.forward_bits(torch.cat((x_conc, x_current), 1), n, l)
+        temp = torch.empty((N, 16, H, W), device=x_current.device, dtype=x_current.dtype)
+        temp[:, 0:2] = mv_before + flow_hat[:, :2]
+        temp[:, 2:4] = mv_after + flow_hat[:, 2:4]
+        temp[:, 4:7], temp[:, 7:10] = x_before, x_after
+        ops.backwarp(x_before, temp[:, 0:2].contiguous(), "flex", out=temp[:, 10:13])
+        ops.backwarp(x_after, temp[:, 2:4].contiguous(), "flex", out=temp[:, 13:16])
+        logits = self.Mask(temp)
+        x_comp, residual, _ = ops.blend_residual("normw", logits, temp[:, 10:13], temp[:, 13:16], x_current)
+        res_hat, ry, rz = self.residual_compressor.forward_bits(residual, n, l)
+        return x_comp + res_hat, (fy + fz) + (ry + rz)
+
+    def forward(self, x_before, x_current, x_after, n=None, l=1, train=False):
+        """b_model.py:49-96: ``size`` per sample (bits), ``rate`` = size / (H*W)."""
+        if train:
+            raise NotImplementedError("b200vc mirrors the inference path (train=False) only")
+        x_hat, bits = self.forward_device(x_before, x_current, x_after, n, l)
+        size = bits.float()
+        return {"x_hat": x_hat, "size": size, "rate": size / (x_current.shape[2] * x_current.shape[3])}

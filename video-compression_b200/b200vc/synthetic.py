@@ -57,6 +57,44 @@ def calibrate_(model, seed=0):
     return model
 
 
+@torch.no_grad()
+def calibrate_flex_(model, seed=0):
+    """Same idea for the Flex-Rate ``BidirFlowRef`` tree: flows of a few pixels, latents over several bins, gain
+    matrices 1 + 0.1*randn (so level interpolation is exercised: SURVEY 8d config 3); un-zeroes the flow
+    compressor's last layer (the reference zero-initialises it, which would make the refinement a no-op)."""
+    g = torch.Generator().manual_seed(seed)
+    randn = lambda *s: torch.randn(*s, generator=g)
+    rand = lambda *s: torch.rand(*s, generator=g)
+
+    def put(p, value):
+        p.copy_(value.to(device=p.device, dtype=p.dtype))
+
+    model.flow_predictor.last.weight.mul_(30.0)
+    model.Mask.last.weight.mul_(30.0)
+    for comp in (model.flow_compressor, model.residual_compressor):
+        comp.g_a[6].weight.mul_(40.0)
+        comp.g_a[6].bias.mul_(40.0)
+        comp.h_a[8].weight.mul_(80.0)
+        comp.h_s[8].weight.mul_(40.0)
+        N = comp.h_s[8].weight.shape[0] // 2
+        put(comp.h_s[8].bias[:N], torch.exp(math.log(0.05) + rand(N) * (math.log(20.0) - math.log(0.05))))
+        for unit in (comp.gain_unit, comp.inv_gain_unit, comp.hyper_gain_unit, comp.hyper_inv_gain_unit):
+            put(unit.gain_matrix, 1.0 + 0.1 * randn(*unit.gain_matrix.shape))
+        for mod in comp.modules():
+            if type(mod).__name__ == "GDN":
+                C = mod.beta.numel()
+                ped = mod.beta_reparam.pedestal.cpu()
+                put(mod.beta, torch.sqrt(torch.max(1.0 + 0.1 * randn(C).abs() + ped, ped)))
+                put(mod.gamma, torch.sqrt(torch.max(0.1 * torch.eye(C) + 0.01 * randn(C, C).abs() + ped, ped)))
+        eb = comp.entropy_bottleneck
+        for i in range(4):
+            f = getattr(eb, f"_factor{i}")
+            put(f, 0.3 * randn(*f.shape))
+    last = model.flow_compressor.g_s[-1][0]
+    put(last.weight, 0.02 * randn(*last.weight.shape))
+    return model
+
+
 def make_sequence(T, H=1080, W=1920, seed=1234, device="cpu", max_motion=8, noise=0.01):
     """[T,3,H,W] fp32 in [0,1]: a smooth random field (bicubic-upsampled uniform noise) seen through a window
     that drifts by up to ``max_motion`` px per frame, plus ``noise`` white noise.
