@@ -174,6 +174,26 @@ B200VC_API int b200vc_sum_partials_f64(const double* partials, int n_per, int n_
 B200VC_API int b200vc_sse_u8_f32(const float* a, const float* b, double* partials, int n_blocks, int N, int C,
                       int H, int W, int h, int w, void* stream);
 
+/* ------------------------------------------------------------------------------------- rANS
+ * Replaces the CPU coder behind `.compress()` / `.decompress()` (compressai.ans BufferedRansEncoder.encode_with_indexes
+ * / RansDecoder.decode_with_indexes; LHBDC/model/layers.py:93-117, LHBDC/encode_B.py:96,104).  The model side is
+ * CompressAI's (16-bit quantised CDF rows, per-symbol row index, offset, tail-bin escape); the container is b200vc's
+ * own ("b2r1": independent streams of stream_len symbols, one thread each) -- see DESIGN.md.
+ *   symbols, indexes int32 [n_symbols]; cdf int32 [rows, cdf_stride]; cdf_len, offset int32 [rows].
+ *   encode: scratch uint16 [n_streams, b200vc_rans_scratch_words(stream_len)], sizes_words int32 [n_streams] (out).
+ *   compact: offsets_words int64 [n_streams] = exclusive prefix sum of sizes_words; out uint16 [sum(sizes)].
+ *   decode: payload/offsets as produced by compact.
+ */
+B200VC_API int b200vc_rans_scratch_words(int stream_len);
+B200VC_API int b200vc_rans_encode(const int32_t* symbols, const int32_t* indexes, const int32_t* cdf,
+                                  const int32_t* cdf_len, const int32_t* offset, int cdf_stride, int64_t n_symbols,
+                                  int stream_len, uint16_t* scratch, int32_t* sizes_words, void* stream);
+B200VC_API int b200vc_rans_compact(const uint16_t* scratch, int stream_len, const int32_t* sizes_words,
+                                   const int64_t* offsets_words, int n_streams, uint16_t* out, void* stream);
+B200VC_API int b200vc_rans_decode(const uint16_t* payload, const int64_t* offsets_words, const int32_t* indexes,
+                                  const int32_t* cdf, const int32_t* cdf_len, const int32_t* offset, int cdf_stride,
+                                  int64_t n_symbols, int stream_len, int32_t* symbols_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

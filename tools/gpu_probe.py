@@ -86,6 +86,15 @@ def section_timing():
         img, flow = warp_case(1, N, 3, 1088, 1920, amp=4.0)
         rec(f"warp_lhbdc N={N}", timeit(lambda: ops.backwarp(img, flow, "lhbdc")), 32 * N * 1088 * 1920,
             timeit(lambda: o_warp.backwarp_lhbdc(img, flow)))
+    def smooth_flow(n, h, w, amp=3.0):
+        f = amp * torch.randn(n, 2, h // 16, w // 16)
+        return torch.nn.functional.interpolate(f, size=(h, w), mode="bilinear", align_corners=False).cuda()
+
+    for N in (1, 4):
+        img, _ = warp_case(1, N, 3, 1088, 1920, amp=4.0)
+        flow = smooth_flow(N, 1088, 1920)
+        for variant in ("lhbdc", "flex", "ac1"):
+            rec(f"warp_{variant} smooth N={N}", timeit(lambda: ops.backwarp(img, flow, variant)), 32 * N * 1088 * 1920)
     img, flow = warp_case(2, 1, 64, 544, 960, amp=4.0)
     rec("warp_ac1 C=64 544x960", timeit(lambda: ops.backwarp(img, flow, "ac1")), 130 * 4 * 544 * 960,
         timeit(lambda: o_warp.warp_ac1(img, flow)))

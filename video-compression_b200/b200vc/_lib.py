@@ -34,6 +34,10 @@ _SIGNATURES = {
     "b200vc_entropy_bottleneck_f32": (c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, c_float, _fp, c_int, c_int, c_int, c_int64, c_void_p]),
     "b200vc_sum_partials_f64": (c_int, [_fp, c_int, c_int, _fp, c_void_p]),
     "b200vc_sse_u8_f32": (c_int, [_fp, _fp, _fp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "b200vc_rans_scratch_words": (c_int, [c_int]),
+    "b200vc_rans_encode": (c_int, [_fp, _fp, _fp, _fp, _fp, c_int, c_int64, c_int, _fp, _fp, c_void_p]),
+    "b200vc_rans_compact": (c_int, [_fp, c_int, _fp, _fp, c_int, _fp, c_void_p]),
+    "b200vc_rans_decode": (c_int, [_fp, _fp, _fp, _fp, _fp, _fp, c_int, c_int64, c_int, _fp, c_void_p]),
 }
 
 EXPORTS = tuple(_SIGNATURES)

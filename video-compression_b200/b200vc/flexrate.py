@@ -117,6 +117,9 @@ class _GainedCompressor(_Compressor):
                             lik_bound=M._lik_bound(gc), inv_gain=self.inv_gain_unit.gain(n, l), want_lik=want_lik)
         return self.g_s(ry["y_hat"]), ry, rz
 
+    def update(self, scale_table=None, force=False):
+        return super().update(scale_table, force)
+
     def forward(self, x, n=None, l=None, train=False):
         """layers.py:135-152 -- API-compatible dict with materialised likelihoods."""
         if train:
@@ -129,9 +132,29 @@ class _GainedCompressor(_Compressor):
         return x_hat, ry["bits"], rz["bits"]
 
     def compress(self, x, n, l):
-        raise NotImplementedError("rANS bitstream production is the 'next' row of SURVEY.md 8f")
+        """layers.py:154-172.  Quirk B.4 is kept: the *unscaled* y is entropy-coded while forward() rates the
+        scaled one."""
+        eb, gc = self.entropy_bottleneck, self.gaussian_conditional
+        y = self.g_a(x)
+        scaled_y = self.gain_unit(y, n, l)
+        z = self.h_a(scaled_y)
+        scaled_z = self.hyper_gain_unit(z, n, l)
+        z_strings = eb.compress(scaled_z)
+        z_hat = eb.decompress(z_strings, z.size()[-2:])
+        scales_hat, means_hat = self.h_s(self.hyper_inv_gain_unit(z_hat, n, l)).chunk(2, 1)
+        indexes = gc.build_indexes(scales_hat)
+        y_strings = gc.compress(y, indexes, means=means_hat)
+        return {"strings": [y_strings, z_strings], "shape": z.size()[-2:]}
 
-    decompress = compress
+    def decompress(self, strings, shape, n, l):
+        """layers.py:174-189."""
+        assert isinstance(strings, list) and len(strings) == 2
+        eb, gc = self.entropy_bottleneck, self.gaussian_conditional
+        z_hat = eb.decompress(strings[1], shape)
+        scales_hat, means_hat = self.h_s(self.hyper_inv_gain_unit(z_hat, n, l)).chunk(2, 1)
+        indexes = gc.build_indexes(scales_hat)
+        y_hat = gc.decompress(strings[0], indexes, means=means_hat)
+        return {"x_hat": self.g_s(self.inv_gain_unit(y_hat, n, l)).clamp_(0, 1)}
 
 
 class FlowCompressor(_GainedCompressor):

@@ -88,13 +88,6 @@ class _Compressor(M.MeanScaleHyperprior):
         self.g_s = nn.Sequential(rb(N, N), ru(N, N, 2), rb(N, N), ru(N, N, 2), rb(N, N), ru(N, N, 2), rb(N, N),
                                  M.subpel_conv3x3(N, io_ch, 2))
 
-    def compress(self, x):
-        raise NotImplementedError(
-            "rANS bitstream production (compressai.ans) is the 'next' row of SURVEY.md 8f; use .symbols(x) for "
-            "the int32 symbols + CDF indexes the coder consumes")
-
-    decompress = compress
-
 
 class MVCompressor(_Compressor):
     def __init__(self, N=128, **kwargs):
@@ -184,6 +177,41 @@ class Model(nn.Module):
         total = bits.sum()
         rate = (total / (N * H * W) / 2.0).float()
         return x_hat, rate, total.item()
+
+
+def _anchor_flows(model, x_before, x_after):
+    """The scripts' version of the anchor-to-anchor prior (encode_B.py:74-79 == decode_B.py:65-70), quirk B.1
+    included: flow_ba is overwritten by pad(flow_ab), so both priors are pad(flow_ab)."""
+    flow_ab = F.avg_pool2d(model.FlowNet(x_after, x_before) / 2., 4)
+    hh, ww = flow_ab.shape[-2:]
+    flow_ba = model.pad(flow_ab)
+    flow_ab = model.pad(flow_ba)
+    return flow_ab, flow_ba, hh, ww
+
+
+def encode_B(model, x_after, x_current, x_before):
+    """``encode_B`` of LHBDC/encode_B.py:71-105: returns (mv_bits, res_bits), each
+    {"strings": [y_strings, z_strings], "shape": z spatial size} with real rANS byte strings."""
+    flow_ab, flow_ba, hh, ww = _anchor_flows(model, x_before, x_after)
+    flow_cb = model.pad(F.avg_pool2d(model.FlowNet(x_current, x_before), 4))
+    flow_ca = model.pad(F.avg_pool2d(model.FlowNet(x_current, x_after), 4))
+    diff_flow = torch.cat([flow_cb - flow_ab, flow_ca - flow_ba], dim=1)
+    flow_hat, _, _ = model.mv_compressor.forward_bits(diff_flow)
+    mv_bits = model.mv_compressor.compress(diff_flow)
+    warped = ops.warp2_lhbdc(x_before, x_after, flow_hat, flow_ab, flow_ba)
+    mask = model.masknet(warped)
+    _, res, _ = ops.blend_residual("mask", mask, warped[:, 0:3], warped[:, 3:6], x_current, want_pred=False)
+    return mv_bits, model.residual_compressor.compress(res)
+
+
+def decode_B(x_before, x_after, model, string_flow, string_res, shape_flow, shape_res):
+    """``decode_B`` of LHBDC/decode_B.py:63-86: the decoded (padded) frame."""
+    flow_ab, flow_ba, hh, ww = _anchor_flows(model, x_before, x_after)
+    flow_hat = model.mv_compressor.decompress(string_flow, shape_flow)["x_hat"]
+    warped = ops.warp2_lhbdc(x_before, x_after, flow_hat, flow_ab, flow_ba)
+    mask = model.masknet(warped)
+    pred, _, _ = ops.blend_residual("mask", mask, warped[:, 0:3], warped[:, 3:6], x_before, want_res=False)
+    return model.residual_compressor.decompress(string_res, shape_res)["x_hat"] + pred
 
 
 def encode_B_symbols(model, x_after, x_current, x_before):

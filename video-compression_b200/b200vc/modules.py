@@ -189,6 +189,43 @@ def eb_forward(mod, x, training=None):
     return r["z_hat"], r["lik"]
 
 
+def eb_tables(mod):
+    """Quantised CDF rows of the factorised prior (EntropyBottleneck.update), cached per weight version."""
+    from . import coding
+    mats = [getattr(mod, f"_matrix{i}") for i in range(5)]
+    bias = [getattr(mod, f"_bias{i}") for i in range(5)]
+    facs = [getattr(mod, f"_factor{i}") for i in range(4)]
+    return _cached(mod, "_b200vc_eb_tables", _pkey(*mats, *bias, *facs, mod.quantiles),
+                   lambda: coding.bottleneck_tables(eb_packed(mod), mod.quantiles, mod.quantiles.device))
+
+
+def _channel_indexes(shape, device):
+    C = shape[1]
+    return torch.arange(C, dtype=torch.int32, device=device).view(1, C, 1, 1).expand(1, C, shape[2], shape[3])
+
+
+def eb_compress(mod, x):
+    """EntropyBottleneck.compress: one byte string per batch item (round(x - median) coded with the channel's CDF)."""
+    from . import coding
+    r = ops.entropy_bottleneck(x, eb_packed(mod), want_z_hat=False, want_lik=False, want_bits=False, want_symbols=True)
+    idx = _channel_indexes(x.shape, x.device)
+    tables = eb_tables(mod)
+    return [coding.rans_encode(r["symbols"][i], idx, tables) for i in range(x.shape[0])]
+
+
+def eb_decompress(mod, strings, size):
+    """EntropyBottleneck.decompress: byte strings + spatial size -> z_hat [N, C, *size]."""
+    from . import coding
+    C = mod.quantiles.shape[0]
+    dev = mod.quantiles.device
+    shape = (1, C, int(size[0]), int(size[1]))
+    idx = _channel_indexes(shape, dev)
+    tables = eb_tables(mod)
+    med = mod.quantiles[:, 0, 1].detach().view(1, C, 1, 1)
+    out = [coding.rans_decode(s, idx, tables).view(shape).float() + med for s in strings]
+    return torch.cat(out, 0)
+
+
 class EntropyBottleneck(EntropyModel):
     def __init__(self, channels, *args, tail_mass=1e-9, init_scale=10, filters=(3, 3, 3, 3), **kwargs):
         super().__init__(*args, **kwargs)
@@ -213,6 +250,13 @@ class EntropyBottleneck(EntropyModel):
         self.register_buffer("target", torch.Tensor([-target, 0, target]))
 
     forward = eb_forward
+    compress = eb_compress
+    decompress = eb_decompress
+
+    def update(self, force=False):
+        """CompressAI rebuilds the quantised CDFs here; b200vc builds them lazily on the device at the first
+        ``compress`` / ``decompress`` (keyed on the parameter versions), so this only reports success."""
+        return True
 
 
 def gc_forward(mod, inputs, scales, means=None, training=None):
@@ -251,6 +295,32 @@ def gc_quantize(mod, inputs, mode, means=None):
                           want_symbols=True, scale_table=tab)["symbols"]
 
 
+def gc_tables(mod):
+    from . import coding
+    if mod.scale_table.numel() < 2:
+        raise RuntimeError("GaussianConditional: call update(force=True) before compress / decompress")
+    return _cached(mod, "_b200vc_gc_tables", _pkey(mod.scale_table),
+                   lambda: coding.gaussian_tables(mod.scale_table.detach().cpu(), mod.scale_table.device,
+                                                  tail_mass=mod.tail_mass, scale_bound=_scale_bound(mod)))
+
+
+def gc_compress(mod, inputs, indexes, means=None):
+    """GaussianConditional.compress: symbols = round(inputs - means) coded with the CDF row ``indexes``."""
+    from . import coding
+    sym = gc_quantize(mod, inputs, "symbols", means)
+    tables = gc_tables(mod)
+    return [coding.rans_encode(sym[i], indexes[i], tables) for i in range(inputs.shape[0])]
+
+
+def gc_decompress(mod, strings, indexes, dtype=torch.float, means=None):
+    """GaussianConditional.decompress: byte strings + indexes (+ means) -> dequantised values."""
+    from . import coding
+    tables = gc_tables(mod)
+    out = torch.stack([coding.rans_decode(s, indexes[i], tables).view(indexes[i].shape)
+                       for i, s in enumerate(strings)], 0).to(dtype)
+    return out + means if means is not None else out
+
+
 class GaussianConditional(EntropyModel):
     def __init__(self, scale_table, *args, scale_bound=0.11, tail_mass=1e-9, **kwargs):
         super().__init__(*args, **kwargs)
@@ -270,6 +340,8 @@ class GaussianConditional(EntropyModel):
     forward = gc_forward
     build_indexes = gc_build_indexes
     quantize = gc_quantize
+    compress = gc_compress
+    decompress = gc_decompress
 
 
 # ----------------------------------------------------------------------------------- hyperprior
@@ -313,6 +385,28 @@ def hyperprior_symbols(mod, x):
             "shape": z.size()[-2:]}
 
 
+def hyperprior_compress(mod, x):
+    """``compress`` of the reference's hyperprior compressors (LHBDC/model/layers.py:93-104)."""
+    y = mod.g_a(x)
+    z = mod.h_a(y)
+    z_strings = mod.entropy_bottleneck.compress(z)
+    z_hat = mod.entropy_bottleneck.decompress(z_strings, z.size()[-2:])
+    scales_hat, means_hat = mod.h_s(z_hat).chunk(2, 1)
+    indexes = mod.gaussian_conditional.build_indexes(scales_hat)
+    y_strings = mod.gaussian_conditional.compress(y, indexes, means=means_hat)
+    return {"strings": [y_strings, z_strings], "shape": z.size()[-2:]}
+
+
+def hyperprior_decompress(mod, strings, shape):
+    """``decompress`` (LHBDC/model/layers.py:106-117)."""
+    assert isinstance(strings, list) and len(strings) == 2
+    z_hat = mod.entropy_bottleneck.decompress(strings[1], shape)
+    scales_hat, means_hat = mod.h_s(z_hat).chunk(2, 1)
+    indexes = mod.gaussian_conditional.build_indexes(scales_hat)
+    y_hat = mod.gaussian_conditional.decompress(strings[0], indexes, means=means_hat)
+    return {"x_hat": mod.g_s(y_hat)}
+
+
 class MeanScaleHyperprior(nn.Module):
     """Container with CompressAI's member names; sub-networks are supplied by the subclasses."""
 
@@ -325,10 +419,12 @@ class MeanScaleHyperprior(nn.Module):
     forward = hyperprior_forward
     forward_bits = hyperprior_forward_bits
     symbols = hyperprior_symbols
+    compress = hyperprior_compress
+    decompress = hyperprior_decompress
 
     def update(self, scale_table=None, force=False):
         """Installs the Gaussian scale table (``model.mv_compressor.update(force=True)``, LHBDC/encode_B.py:34).
-        The quantised-CDF build that real rANS coding needs belongs to the entropy-coder row."""
+        The quantised CDF rows are built lazily on the device at the first compress / decompress."""
         if scale_table is None:
             scale_table = get_scale_table()
         return self.gaussian_conditional.update_scale_table(scale_table, force=force)

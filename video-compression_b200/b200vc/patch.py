@@ -35,10 +35,14 @@ def patch(model, fuse=True):
             _bind(mod, "forward", modules.res_upsample_forward)
         elif cls == "EntropyBottleneck":
             _bind(mod, "forward", modules.eb_forward)
+            _bind(mod, "compress", modules.eb_compress)
+            _bind(mod, "decompress", modules.eb_decompress)
         elif cls == "GaussianConditional":
             _bind(mod, "forward", modules.gc_forward)
             _bind(mod, "build_indexes", modules.gc_build_indexes)
             _bind(mod, "quantize", modules.gc_quantize)
+            _bind(mod, "compress", modules.gc_compress)
+            _bind(mod, "decompress", modules.gc_decompress)
         if hasattr(mod, "entropy_bottleneck") and hasattr(mod, "gaussian_conditional") and hasattr(mod, "g_a"):
             _bind(mod, "forward_bits", modules.hyperprior_forward_bits)
             _bind(mod, "symbols", modules.hyperprior_symbols)
