@@ -116,7 +116,9 @@ def test_hyperprior_compress_decompress(models):
     real = 8 * (len(out["strings"][0][0]) + len(out["strings"][1][0]))
     est = (by + bz).item()
     print(f"hyperprior: estimated {est:.0f} bits, coded {real} bits ({real / est:.4f}x)")
-    assert 0.95 * est < real < 1.1 * est + 2048
+    # random (untrained) weights put many latents far outside their predicted scale: the estimate floors such
+    # symbols at 1e-9 (29.9 bits) while the coder pays the tail bin + a 32-bit raw escape (~48 bits)
+    assert 0.95 * est < real < 1.5 * est + 2048
 
 
 def test_encode_b_decode_b_round_trip(models, tmp_path, golden_dir):
