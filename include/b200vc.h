@@ -97,6 +97,16 @@ B200VC_API int b200vc_warp2_lhbdc_f32(const float* x_before, const float* x_afte
                            const float* tab_y, float* out, float* flows_out, int N, int H, int W, int h4,
                            int w4, int arith, void* stream);
 
+/* Search form (ICIP2024/src/opt_helpers.py:23-51: prediction_flowonly + clamp + MSE per candidate down-ratio;
+ * OJSP2025/video_model.py:621-666): both warps + 0.5/0.5 blend + clamp + squared error against x_cur in one pass.
+ *   x1, x2, x_cur [N,3,H,W]; flow1, flow2 [N,2,H,W]; pred (nullable) [N,3,H,W];
+ *   partials double[N * b200vc_warp2_half_sse_blocks(H, W)]: per-CTA SSE, reduce with b200vc_sum_partials_f64.
+ */
+B200VC_API int b200vc_warp2_half_sse_blocks(int H, int W);
+B200VC_API int b200vc_warp2_half_sse_f32(const float* x1, const float* x2, const float* flow1, const float* flow2,
+                                         const float* x_cur, const float* tab_x, const float* tab_y, float* pred,
+                                         double* partials, int N, int H, int W, int variant, void* stream);
+
 /* ------------------------------------------------------------------------------------ blend / residual
  * Replaces LHBDC/model/m.py:63-67, Flex-Rate.../b_model/b_model.py:68-73, ICIP2024/src/opt_helpers.py:35-45.
  *   a, b: the two warped references [N,3,H,W] (batch strides a_bs, b_bs: may be halves of the concat

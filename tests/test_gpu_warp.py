@@ -128,3 +128,23 @@ def test_warp2_matches_unfused_reference_chain(shape):
     again = torch.cat([ops.backwarp(xb, flows[:, :2].contiguous(), "lhbdc"),
                        ops.backwarp(xa, flows[:, 2:].contiguous(), "lhbdc")], 1)
     assert torch.equal(got, again)
+
+
+@pytest.mark.parametrize("shape", [(1, 1088, 1920), (2, 45, 70)])
+def test_search_form_warp_blend_sse(shape):
+    """ICIP2024/src/opt_helpers.py:23-51 (prediction_flowonly + clamp + MSE) as one kernel."""
+    from b200vc import ops
+    N, H, W = shape
+    x1, f1 = warp_case(31, N, 3, H, W, amp=3.0)
+    x2, f2 = warp_case(32, N, 3, H, W, amp=3.0)
+    xc = torch.rand(N, 3, H, W, device="cuda")
+    want_pred = 0.5 * o_warp.warp_ac1(x1 * 1.3 - 0.1, f1) + (1 - 0.5) * o_warp.warp_ac1(x2, f2)
+    sse, pred = ops.warp2_half_sse(x1 * 1.3 - 0.1, x2, f1, f2, xc, "ac1", want_pred=True)
+    assert torch.equal(pred, want_pred)
+    for n in range(N):
+        want = ((torch.clamp(want_pred[n], 0, 1) - xc[n]).double() ** 2).sum().item()
+        assert abs(sse[n].item() - want) / want < 1e-6
+    mse = o_warp.blend_half_mse(o_warp.warp_ac1(x1 * 1.3 - 0.1, f1), o_warp.warp_ac1(x2, f2), xc).item()
+    assert abs(sse.sum().item() / xc.numel() - mse) / mse < 1e-5
+    sse2, none = ops.warp2_half_sse(x1 * 1.3 - 0.1, x2, f1, f2, xc, "ac1")
+    assert none is None and torch.equal(sse, sse2)

@@ -169,6 +169,28 @@ def warp2_lhbdc(x_before, x_after, flow_hat, flow_ab, flow_ba, return_flows=Fals
     return (out, flows) if return_flows else out
 
 
+def warp2_half_sse(x1, x2, flow1, flow2, x_cur, variant="ac1", want_pred=False):
+    """Search form of ICIP2024/src/opt_helpers.py:23-51: warp both references, 0.5/0.5 blend, clamp, squared error
+    against ``x_cur`` -- one kernel.  Returns (sse[N] float64, pred or None); MSE = sse / (3*H*W)."""
+    if variant not in _VARIANTS:
+        raise ValueError(f"warp2_half_sse: unknown variant {variant!r}")
+    x1, x2, xc = (_contig(t, "warp2_half_sse(img)") for t in (x1, x2, x_cur))
+    f1, f2 = _contig(flow1, "warp2_half_sse(flow1)"), _contig(flow2, "warp2_half_sse(flow2)")
+    N, C, H, W = x1.shape
+    if C != 3 or x2.shape != x1.shape or xc.shape != x1.shape or tuple(f1.shape) != (N, 2, H, W) or f2.shape != f1.shape:
+        raise RuntimeError("warp2_half_sse: expected [N,3,H,W] images and [N,2,H,W] flows")
+    tx, ty = (None, None) if variant == "flex" else grid_tables(variant, H, W, x1.device)
+    lib = _lib.load()
+    nb = lib.b200vc_warp2_half_sse_blocks(H, W)
+    part = torch.empty(N * nb, device=x1.device, dtype=torch.float64)
+    pred = torch.empty_like(x1) if want_pred else None
+    p = lambda t: t.data_ptr() if t is not None else None
+    _run("warp2_half_sse_f32", (13 + 3 * int(want_pred)) * 4 * N * H * W, lambda: lib.b200vc_warp2_half_sse_f32(
+        x1.data_ptr(), x2.data_ptr(), f1.data_ptr(), f2.data_ptr(), xc.data_ptr(), p(tx), p(ty), p(pred),
+        part.data_ptr(), N, H, W, _VARIANTS[variant], _stream()))
+    return sum_partials(part, nb, N), pred
+
+
 # ------------------------------------------------------------------------------- blend / residual
 def reduce_blocks(elems_per_sample):
     return _lib.load().b200vc_reduce_blocks(int(elems_per_sample))

@@ -51,7 +51,7 @@ struct Cfg {
   static constexpr int kRawOff = 0;
   static constexpr int kAbOff = R * kTileBytes;              // A x (hi | lo)
   static constexpr int kBarOff = kAbOff + A * 2 * kTileBytes;
-  static constexpr int kNumBars = 2 * R + 2 * A + 4;
+  static constexpr int kNumBars = 2 * R + 2 * A + 5;
   static constexpr int kSmemBytes = kBarOff + 8 * kNumBars + 16 + 1024 /*alignment slack*/;
 };
 
@@ -198,6 +198,7 @@ gdn_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
   auto ab_empty = [&](int a) { return bar_base + 8 * (2 * R + A + a); };
   auto d_full = [&](int d) { return bar_base + 8 * (2 * R + 2 * A + d); };
   auto d_empty = [&](int d) { return bar_base + 8 * (2 * R + 2 * A + 2 + d); };
+  const uint32_t gamma_ready = bar_base + 8 * (2 * R + 2 * A + 4);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + CFG::kBarOff + 8 * CFG::kNumBars);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -215,6 +216,7 @@ gdn_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
       mbar_init(d_full(d), 1);
       mbar_init(d_empty(d), kEpiWarps);
     }
+    mbar_init(gamma_ready, kEpiWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_out)) : "memory");
@@ -249,10 +251,10 @@ gdn_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
       tmem_st32(tmem + ((uint32_t)(32 * q) << 16) + (which ? kColGlo : kColGhi) + part * 32, v);
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(gamma_ready);  // only the MMA issuer waits for it: loads and the split start now
   }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -275,6 +277,8 @@ gdn_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
+      mbar_wait(gamma_ready, 0);
+      tc_fence_after();
       int k = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++k) {
         const int a = k % A, pa = (k / A) & 1, d = k & 1, pd = (k >> 1) & 1;

@@ -282,6 +282,51 @@ warp2_lhbdc_kernel(const float* __restrict__ xb, const float* __restrict__ xa,
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Search form (ICIP2024/src/opt_helpers.py:23-51, OJSP2025/video_model.py:621-666): for every candidate
+// down-ratio the reference warps both references, blends 0.5/0.5, clamps and takes the MSE against the current
+// frame -- four full-frame tensors written and re-read per candidate.  Here: both warps + blend + clamp + squared
+// error in one pass, nothing but per-CTA fp64 partials written (52 B/px algorithmic instead of 156+).
+template <int VARIANT>
+__global__ void __launch_bounds__(kWarpThreads)
+warp2_half_sse_kernel(const float* __restrict__ x1, const float* __restrict__ x2, const float* __restrict__ flow1,
+                      const float* __restrict__ flow2, const float* __restrict__ x_cur,
+                      const float* __restrict__ tab_x, const float* __restrict__ tab_y, float* __restrict__ pred_out,
+                      double* __restrict__ partials, WarpGeom g) {
+  constexpr bool BORDER = (VARIANT != B200VC_WARP_FLEX);
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * (kWarpThreads / 32) + (threadIdx.x >> 5);
+  const int n = blockIdx.z;
+  const int HW = g.H * g.W;
+  float sse = 0.f;
+  if (x < g.W && y < g.H) {
+    const int o = y * g.W + x;
+    const float tx = BORDER ? __ldg(tab_x + x) : 0.f, ty = BORDER ? __ldg(tab_y + y) : 0.f;
+    float r[2][3];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const float* f = (k == 0 ? flow1 : flow2) + (int64_t)n * 2 * HW + o;
+      float ix, iy;
+      coords<VARIANT, true>(g, x, y, __ldg(f), __ldg(f + HW), tx, ty, ix, iy);
+      const Taps t = make_taps<BORDER>(ix, iy, g.H, g.W);
+      const float* ip = (k == 0 ? x1 : x2) + (int64_t)n * 3 * HW;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) r[k][c] = sample<BORDER>(ip + (int64_t)c * HW, t);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      // mask*wref1 + (1-mask)*wref2 with mask = 0.5: both products exact, one rounding
+      const float pred = __fadd_rn(__fmul_rn(0.5f, r[0][c]), __fmul_rn(0.5f, r[1][c]));
+      if (pred_out != nullptr) pred_out[((int64_t)n * 3 + c) * HW + o] = pred;
+      const float d = __fsub_rn(fminf(fmaxf(pred, 0.f), 1.f), __ldg(x_cur + ((int64_t)n * 3 + c) * HW + o));
+      sse = __fmaf_rn(d, d, sse);
+    }
+  }
+  const double tot = block_sum_to_f64<kWarpThreads>(sse);
+  if (threadIdx.x == 0)
+    partials[((int64_t)n * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = tot;
+}
+
 static WarpGeom make_geom(int H, int W, int variant, int arith) {
   WarpGeom g;
   g.H = H;
@@ -380,4 +425,30 @@ extern "C" int b200vc_warp2_lhbdc_f32(const float* x_before, const float* x_afte
     warp2_lhbdc_kernel<false><<<grid, kWarpThreads, 0, (cudaStream_t)stream>>>(
         x_before, x_after, flow_hat, flow_ab, flow_ba, tab_x, tab_y, out, flows_out, h4, w4, g);
   return check_launch("warp2_lhbdc_f32");
+}
+
+extern "C" int b200vc_warp2_half_sse_blocks(int H, int W) {
+  if (H <= 0 || W <= 0) return 0;
+  return ((W + 31) / 32) * ((H + kWarpThreads / 32 - 1) / (kWarpThreads / 32));
+}
+
+extern "C" int b200vc_warp2_half_sse_f32(const float* x1, const float* x2, const float* flow1, const float* flow2,
+                                         const float* x_cur, const float* tab_x, const float* tab_y, float* pred,
+                                         double* partials, int N, int H, int W, int variant, void* stream) {
+  B200VC_REQUIRE(x1 && x2 && flow1 && flow2 && x_cur && partials, "warp2_half_sse_f32: null pointer");
+  B200VC_REQUIRE(N > 0 && N <= 65535 && H > 0 && W > 0, "warp2_half_sse_f32: bad shape");
+  B200VC_REQUIRE(variant >= 0 && variant <= 2, "warp2_half_sse_f32: unknown variant %d", variant);
+  B200VC_REQUIRE(variant == B200VC_WARP_FLEX || (tab_x && tab_y), "warp2_half_sse_f32: grid tables required");
+  B200VC_REQUIRE((int64_t)H * W < (1ll << 31), "warp2_half_sse_f32: plane too large");
+  const WarpGeom g = make_geom(H, W, variant, 0);
+  const int rows = kWarpThreads / 32;
+  dim3 grid((W + 31) / 32, (H + rows - 1) / rows, N);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (variant == B200VC_WARP_LHBDC)
+    warp2_half_sse_kernel<0><<<grid, kWarpThreads, 0, st>>>(x1, x2, flow1, flow2, x_cur, tab_x, tab_y, pred, partials, g);
+  else if (variant == B200VC_WARP_FLEX)
+    warp2_half_sse_kernel<1><<<grid, kWarpThreads, 0, st>>>(x1, x2, flow1, flow2, x_cur, tab_x, tab_y, pred, partials, g);
+  else
+    warp2_half_sse_kernel<2><<<grid, kWarpThreads, 0, st>>>(x1, x2, flow1, flow2, x_cur, tab_x, tab_y, pred, partials, g);
+  return check_launch("warp2_half_sse_f32");
 }
