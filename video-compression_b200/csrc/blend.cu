@@ -91,31 +91,37 @@ blend_kernel(int mode, const float* __restrict__ mask, const float* __restrict__
 }
 
 // uint8-domain SSE over the crop [:h,:w] of every plane: float_to_uint8 = round(clip(x,0,1)*255) (half-even).
+// One CTA walks whole rows (no per-element div/mod), 128-bit loads when the row start is 16-byte aligned.
+__device__ __forceinline__ float sq_u8_diff(float a, float b) {
+  const float qa = rintf(__fmul_rn(fminf(fmaxf(a, 0.f), 1.f), 255.f));
+  const float qb = rintf(__fmul_rn(fminf(fmaxf(b, 0.f), 1.f), 255.f));
+  const float d = qa - qb;
+  return d * d;  // exact integer <= 65025
+}
+
 __global__ void __launch_bounds__(kBlendThreads)
 sse_u8_kernel(const float* __restrict__ a, const float* __restrict__ b, double* __restrict__ partials,
               int planes, int H, int W, int h, int w) {
-  const int64_t total = (int64_t)planes * h * w;
-  float acc = 0.f;  // integer-valued; flushed to fp64 every 128 terms (128 * 255^2 < 2^24, so exact)
+  const int rows = planes * h;
+  const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15u) == 0;
+  const int w4 = vec ? (w / 4) : 0;
   double dacc = 0.0;
-  int cnt = 0;
-  for (int64_t i = (int64_t)blockIdx.x * kBlendThreads + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * kBlendThreads) {
-    const int xx = (int)(i % w);
-    const int64_t r = i / w;
-    const int yy = (int)(r % h);
-    const int64_t pl = r / h;
-    const int64_t o = (pl * H + yy) * (int64_t)W + xx;
-    const float qa = rintf(__fmul_rn(fminf(fmaxf(__ldg(a + o), 0.f), 1.f), 255.f));
-    const float qb = rintf(__fmul_rn(fminf(fmaxf(__ldg(b + o), 0.f), 1.f), 255.f));
-    const float d = qa - qb;
-    acc += d * d;  // exact: integers, flushed to double before exceeding 2^24
-    if (++cnt == 128) {
-      dacc += (double)acc;
-      acc = 0.f;
-      cnt = 0;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int pl = row / h, yy = row - pl * h;
+    const int64_t o = ((int64_t)pl * H + yy) * W;
+    float acc = 0.f;  // <= (4 + 1) elements per thread per row at 1080p: far below 2^24 / 65025 = 258 terms
+    int cnt = 0;
+    for (int x4 = threadIdx.x; x4 < w4; x4 += kBlendThreads) {
+      const float4 va = ld_stream4(a + o + 4 * x4), vb = ld_stream4(b + o + 4 * x4);
+      acc += sq_u8_diff(va.x, vb.x) + sq_u8_diff(va.y, vb.y) + sq_u8_diff(va.z, vb.z) + sq_u8_diff(va.w, vb.w);
+      if ((cnt += 4) >= 252) { dacc += (double)acc; acc = 0.f; cnt = 0; }
     }
+    for (int x = 4 * w4 + threadIdx.x; x < w; x += kBlendThreads) {
+      acc += sq_u8_diff(__ldg(a + o + x), __ldg(b + o + x));
+      if (++cnt >= 252) { dacc += (double)acc; acc = 0.f; cnt = 0; }
+    }
+    dacc += (double)acc;
   }
-  dacc += (double)acc;
   __shared__ double s_part[kBlendThreads / 32];
   double d = warp_sum(dacc);
   if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = d;
