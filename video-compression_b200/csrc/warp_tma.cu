@@ -88,8 +88,7 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap map_img, const float* __rest
     for (int w = 1; w < kThreads / 32; ++w) {
       a = min(a, s_red[w][0]); b = max(b, s_red[w][1]); c = min(c, s_red[w][2]); d = max(d, s_red[w][3]);
     }
-    // the box start must keep the 16-byte alignment TMA needs for its inner coordinate? no: any element coordinate
-    // is legal; only the global strides and the smem destination are alignment-constrained
+    if (g.arith == 0) a &= ~3;  // start the box on a 16-byte boundary of the row (arith != 0 here: debug switch)
     const bool fits = (b + 1 - a + 1 <= kBW) && (d + 1 - c + 1 <= kBH) && a > -(1 << 20) && c > -(1 << 20) &&
                       b < (1 << 20) && d < (1 << 20);
     s_box[0] = a; s_box[1] = c; s_box[2] = fits ? 1 : 0;
@@ -207,6 +206,12 @@ int launch_warp_tma(const float* img, int64_t img_bs, const float* flow, const f
   int dev = 0;
   cudaGetDevice(&dev);
   dim3 grid((W + kTW - 1) / kTW, (H + kTH - 1) / kTH, N);
+  WarpGeom gd = g;
+  static const int unaligned = []() {
+    const char* e = getenv("B200VC_WARP_TMA_UNALIGNED");
+    return e ? atoi(e) : 0;
+  }();
+  gd.arith = unaligned;  // the TMA kernel always uses the production arithmetic; the field is reused as a debug switch
 #define B200VC_WT_LAUNCH(V)                                                                                     \
   do {                                                                                                          \
     if (dev >= 0 && dev < 64 && !configured[dev][V]) {                                                          \
@@ -217,7 +222,7 @@ int launch_warp_tma(const float* img, int64_t img_bs, const float* flow, const f
       }                                                                                                         \
       configured[dev][V] = true;                                                                                \
     }                                                                                                           \
-    warp_tma_kernel<V><<<grid, kThreads, kSmemBytes, st>>>(map, img, flow, tab_x, tab_y, out, out_bs, g);        \
+    warp_tma_kernel<V><<<grid, kThreads, kSmemBytes, st>>>(map, img, flow, tab_x, tab_y, out, out_bs, gd);        \
   } while (0)
   if (g.variant == B200VC_WARP_LHBDC) B200VC_WT_LAUNCH(0);
   else if (g.variant == B200VC_WARP_FLEX) B200VC_WT_LAUNCH(1);
