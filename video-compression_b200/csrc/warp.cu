@@ -21,6 +21,9 @@
 
 namespace b200vc {
 
+int launch_warp2_tma(const float* xb, const float* xa, const float* flow_hat, const float* flow_ab,
+                     const float* flow_ba, const float* tab_x, const float* tab_y, float* out, float* flows_out, int N,
+                     int H, int W, int h4, int w4, const WarpGeom& g, cudaStream_t st);  // warp_tma.cu
 int launch_warp_tma(const float* img, int64_t img_bs, const float* flow, const float* tab_x, const float* tab_y,
                     float* out, int64_t out_bs, int N, int C, int H, int W, const WarpGeom& g, cudaStream_t st);  // warp_tma.cu
 
@@ -88,33 +91,6 @@ warp_kernel(const float* __restrict__ img, int64_t img_bs, const float* __restri
 // ATen upsample_bilinear2d (align_corners=False, scale_factor=4 => rscale = 0.25):
 //   src = max(0.25*(dst+0.5) - 0.5, 0); i0 = (int)src; ip = i0 < in-1; l1 = src - i0; l0 = 1 - l1
 //   val = l0y*(l0x*a + l1x*b) + l1y*(l0x*c + l1x*d)
-struct Up4 {
-  int i0, i1;
-  float l0, l1;
-};
-__device__ __forceinline__ Up4 up4_index(int dst, int in_size) {
-  Up4 r;
-  float src = __fmaf_rn(0.25f, (float)dst + 0.5f, -0.5f);
-  src = src < 0.f ? 0.f : src;
-  r.i0 = (int)src;
-  r.i1 = r.i0 + ((r.i0 < in_size - 1) ? 1 : 0);
-  r.l1 = __fsub_rn(src, (float)r.i0);
-  r.l0 = __fsub_rn(1.f, r.l1);
-  return r;
-}
-
-__device__ __forceinline__ float up4_value(const Up4& uy, const Up4& ux, float a, float b, float c, float d,
-                                           int arith) {
-  if (arith & B200VC_ARITH_NO_FMA) {
-    const float top = __fadd_rn(__fmul_rn(ux.l0, a), __fmul_rn(ux.l1, b));
-    const float bot = __fadd_rn(__fmul_rn(ux.l0, c), __fmul_rn(ux.l1, d));
-    return __fadd_rn(__fmul_rn(uy.l0, top), __fmul_rn(uy.l1, bot));
-  }
-  const float top = __fmaf_rn(ux.l0, a, __fmul_rn(ux.l1, b));
-  const float bot = __fmaf_rn(ux.l0, c, __fmul_rn(ux.l1, d));
-  return __fmaf_rn(uy.l0, top, __fmul_rn(uy.l1, bot));
-}
-
 // CTA = 32 x 8 output pixels.  The quarter-resolution flow (mv x_hat + linear-motion prior, m.py:56,58) that the
 // tile's x4 upsample touches -- at most 10 x 4 points x 4 channels -- is summed once into shared memory; every
 // pixel then reads its four corners from there (warp-wide broadcasts) instead of 32 global loads.
@@ -314,6 +290,11 @@ extern "C" int b200vc_warp2_lhbdc_f32(const float* x_before, const float* x_afte
   const WarpGeom g = make_geom(H, W, B200VC_WARP_LHBDC, arith);
   const int rows = kWarpThreads / 32;
   dim3 grid((W + 31) / 32, (H + rows - 1) / rows, N);
+  if (arith == 0) {
+    const int rc = launch_warp2_tma(x_before, x_after, flow_hat, flow_ab, flow_ba, tab_x, tab_y, out, flows_out, N, H, W,
+                                    h4, w4, g, (cudaStream_t)stream);
+    if (rc != B200VC_EUNSUPPORTED) return rc;
+  }
   if (arith == 0)
     warp2_lhbdc_kernel<true><<<grid, kWarpThreads, 0, (cudaStream_t)stream>>>(
         x_before, x_after, flow_hat, flow_ab, flow_ba, tab_x, tab_y, out, flows_out, h4, w4, g);

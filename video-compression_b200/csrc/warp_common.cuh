@@ -118,4 +118,35 @@ __device__ __forceinline__ void coords(const WarpGeom& g, int x, int y, float u,
 }
 
 
+// ATen upsample_bilinear2d (align_corners=False, scale_factor=4 => rscale = 0.25):
+//   src = max(0.25*(dst+0.5) - 0.5, 0); i0 = (int)src; ip = i0 < in-1; l1 = src - i0; l0 = 1 - l1
+//   val = l0y*(l0x*a + l1x*b) + l1y*(l0x*c + l1x*d)
+struct Up4 {
+  int i0, i1;
+  float l0, l1;
+};
+__device__ __forceinline__ Up4 up4_index(int dst, int in_size) {
+  Up4 r;
+  float src = __fmaf_rn(0.25f, (float)dst + 0.5f, -0.5f);
+  src = src < 0.f ? 0.f : src;
+  r.i0 = (int)src;
+  r.i1 = r.i0 + ((r.i0 < in_size - 1) ? 1 : 0);
+  r.l1 = __fsub_rn(src, (float)r.i0);
+  r.l0 = __fsub_rn(1.f, r.l1);
+  return r;
+}
+
+__device__ __forceinline__ float up4_value(const Up4& uy, const Up4& ux, float a, float b, float c, float d,
+                                           int arith) {
+  if (arith & B200VC_ARITH_NO_FMA) {
+    const float top = __fadd_rn(__fmul_rn(ux.l0, a), __fmul_rn(ux.l1, b));
+    const float bot = __fadd_rn(__fmul_rn(ux.l0, c), __fmul_rn(ux.l1, d));
+    return __fadd_rn(__fmul_rn(uy.l0, top), __fmul_rn(uy.l1, bot));
+  }
+  const float top = __fmaf_rn(ux.l0, a, __fmul_rn(ux.l1, b));
+  const float bot = __fmaf_rn(ux.l0, c, __fmul_rn(ux.l1, d));
+  return __fmaf_rn(uy.l0, top, __fmul_rn(uy.l1, bot));
+}
+
+
 }  // namespace b200vc

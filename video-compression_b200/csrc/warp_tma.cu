@@ -162,6 +162,156 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap map_img, const float* __rest
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Fused LHBDC motion compensation (LHBDC/model/m.py:55-63) with TMA-staged taps: per direction, the x4-upsampled
+// flow (from the shared-memory quarter-resolution tile, as in warp.cu's warp2 kernel) -> coordinates -> bounding
+// box -> one 3-D TMA box -> taps from shared memory.  The two directions reuse the box buffer (barrier phase = dir).
+constexpr int kQW2 = kTW / 4 + 2, kQH2 = kTH / 4 + 2;  // 18 x 10 quarter-res points per channel
+
+__global__ void __launch_bounds__(kThreads, 3)
+warp2_tma_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_a,
+                 const float* __restrict__ xb, const float* __restrict__ xa, const float* __restrict__ flow_hat,
+                 const float* __restrict__ flow_ab, const float* __restrict__ flow_ba,
+                 const float* __restrict__ tab_x, const float* __restrict__ tab_y, float* __restrict__ out,
+                 float* __restrict__ flows_out, int h4, int w4, WarpGeom g) {
+  extern __shared__ uint8_t smem_raw[];
+  float* tile = reinterpret_cast<float*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
+  __shared__ float s_q[4][kQH2][kQW2];
+  __shared__ int s_red[kThreads / 32][4];
+  __shared__ int s_box[3];
+  __shared__ __align__(8) uint64_t s_bar;
+
+  const int tid = threadIdx.x;
+  const int tx = tid & (kTW - 1), ty = tid >> 6;
+  const int bx = blockIdx.x * kTW, by = blockIdx.y * kTH;
+  const int x = bx + tx;
+  const int n = blockIdx.z;
+  const int HW = g.H * g.W;
+  const int hh = g.H / 4, ww = g.W / 4;
+  const int q = h4 * w4;
+  const bool xin = x < g.W;
+  const int xc = xin ? x : g.W - 1;
+
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // quarter-res flow = mv x_hat chunk + linear-motion prior (one rounded add each, as torch does)
+  const int qx0 = up4_index(bx, ww).i0, qy0 = up4_index(by, hh).i0;
+  for (int e = tid; e < 4 * kQH2 * kQW2; e += kThreads) {
+    const int ch = e / (kQH2 * kQW2), r = (e / kQW2) % kQH2, c = e % kQW2;
+    const int sy = min(qy0 + r, hh - 1), sx = min(qx0 + c, ww - 1);
+    const float* pri = (ch < 2 ? flow_ab : flow_ba) + ((int64_t)n * 2 + (ch & 1)) * q;
+    const float* hat = flow_hat + ((int64_t)n * 4 + ch) * q;
+    s_q[ch][r][c] = __fadd_rn(__ldg(hat + sy * w4 + sx), __ldg(pri + sy * w4 + sx));
+  }
+  __syncthreads();
+
+  const Up4 ux = up4_index(xc, ww);
+  const int cx0 = ux.i0 - qx0, cx1 = ux.i1 - qx0;
+  const float txv = __ldg(tab_x + xc);
+  float* op = out + (int64_t)n * 6 * HW;
+
+#pragma unroll 1
+  for (int dir = 0; dir < 2; ++dir) {
+    float ix[kPX], iy[kPX];
+    int mnx = 0x7fffffff, mxx = -0x7fffffff - 1, mny = 0x7fffffff, mxy = -0x7fffffff - 1;
+#pragma unroll
+    for (int k = 0; k < kPX; ++k) {
+      const int yr = by + ty + 4 * k;
+      const int y = min(yr, g.H - 1);
+      const Up4 uy = up4_index(y, hh);
+      const int cy0 = uy.i0 - qy0, cy1 = uy.i1 - qy0;
+      const float u = up4_value(uy, ux, s_q[2 * dir][cy0][cx0], s_q[2 * dir][cy0][cx1], s_q[2 * dir][cy1][cx0],
+                                s_q[2 * dir][cy1][cx1], 0);
+      const float v = up4_value(uy, ux, s_q[2 * dir + 1][cy0][cx0], s_q[2 * dir + 1][cy0][cx1],
+                                s_q[2 * dir + 1][cy1][cx0], s_q[2 * dir + 1][cy1][cx1], 0);
+      if (flows_out != nullptr && xin && yr < g.H) {
+        float* fo = flows_out + ((int64_t)n * 4 + dir * 2) * HW + yr * g.W + x;
+        fo[0] = u;
+        fo[HW] = v;
+      }
+      coords<B200VC_WARP_LHBDC, true>(g, xc, y, u, v, txv, __ldg(tab_y + y), ix[k], iy[k]);
+      const int x0 = (int)floorf(ix[k]), y0 = (int)floorf(iy[k]);
+      mnx = min(mnx, x0); mxx = max(mxx, x0);
+      mny = min(mny, y0); mxy = max(mxy, y0);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mnx = min(mnx, __shfl_xor_sync(0xffffffffu, mnx, o)); mxx = max(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+      mny = min(mny, __shfl_xor_sync(0xffffffffu, mny, o)); mxy = max(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+    }
+    if ((tid & 31) == 0) {
+      s_red[tid >> 5][0] = mnx; s_red[tid >> 5][1] = mxx; s_red[tid >> 5][2] = mny; s_red[tid >> 5][3] = mxy;
+    }
+    __syncthreads();  // also: every thread has finished reading the box of the previous direction
+    if (tid == 0) {
+      int a = s_red[0][0], b = s_red[0][1], c = s_red[0][2], d = s_red[0][3];
+      for (int w = 1; w < kThreads / 32; ++w) {
+        a = min(a, s_red[w][0]); b = max(b, s_red[w][1]); c = min(c, s_red[w][2]); d = max(d, s_red[w][3]);
+      }
+      a &= ~3;  // TMA: the innermost start coordinate must sit on a 16-byte boundary (unaligned starts fault)
+      const bool fits = (b + 1 - a + 1 <= kBW) && (d + 1 - c + 1 <= kBH);
+      s_box[0] = a; s_box[1] = c; s_box[2] = fits ? 1 : 0;
+      if (fits) {
+        const uint32_t bar = smem_u32(&s_bar);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kBoxBytes) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+            ::"r"(smem_u32(tile)), "l"(reinterpret_cast<uint64_t>(dir == 0 ? &map_b : &map_a)), "r"(bar), "r"(a),
+              "r"(c), "r"(n * 3)
+            : "memory");
+      }
+    }
+    __syncthreads();
+    const int bx0 = s_box[0], by0 = s_box[1];
+    const bool staged = s_box[2] != 0;
+    if (staged) {
+      const uint32_t bar = smem_u32(&s_bar);
+      uint32_t done = 0;
+      for (uint32_t spins = 0; !done; ++spins) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(dir) : "memory");
+        if (spins > (1u << 26)) __trap();
+      }
+    }
+    const float* ip = (dir == 0 ? xb : xa) + (int64_t)n * 3 * HW;
+#pragma unroll
+    for (int k = 0; k < kPX; ++k) {
+      const int y = by + ty + 4 * k;
+      float r[3];
+      if (staged) {
+        const float fx = floorf(ix[k]), fy = floorf(iy[k]);
+        const int x0 = (int)fx, y0 = (int)fy;
+        const float dx1 = __fsub_rn((float)(x0 + 1), ix[k]), dx0 = __fsub_rn(ix[k], (float)x0);
+        const float dy1 = __fsub_rn((float)(y0 + 1), iy[k]), dy0 = __fsub_rn(iy[k], (float)y0);
+        const float w00 = __fmul_rn(dx1, dy1), w01 = __fmul_rn(dx0, dy1);
+        const float w10 = __fmul_rn(dx1, dy0), w11 = __fmul_rn(dx0, dy0);
+        const float* t0 = tile + (y0 - by0) * kBW + (x0 - bx0);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float* t = t0 + c * (kBH * kBW);
+          float acc = __fmaf_rn(t[0], w00, 0.f);
+          acc = __fmaf_rn(t[1], w01, acc);
+          acc = __fmaf_rn(t[kBW], w10, acc);
+          r[c] = __fmaf_rn(t[kBW + 1], w11, acc);
+        }
+      } else {
+        const Taps t = make_taps<true>(ix[k], iy[k], g.H, g.W);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) r[c] = sample<true>(ip + (int64_t)c * HW, t);
+      }
+      if (xin && y < g.H) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) op[(int64_t)(dir * 3 + c) * HW + y * g.W + x] = r[c];
+      }
+    }
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -176,6 +326,18 @@ static EncodeTiledFn encode_fn() {
       fn = reinterpret_cast<EncodeTiledFn>(p);
   }
   return fn;
+}
+
+static bool make_img_map(CUtensorMap* map, const float* img, int N, int H, int W) {
+  EncodeTiledFn enc = encode_fn();
+  if (enc == nullptr) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N * 3};
+  cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4};
+  cuuint32_t box[3] = {kBW, kBH, 3};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(img), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace wt
@@ -229,6 +391,35 @@ int launch_warp_tma(const float* img, int64_t img_bs, const float* flow, const f
   else B200VC_WT_LAUNCH(2);
 #undef B200VC_WT_LAUNCH
   return check_launch("warp_f32(tma)");
+}
+
+int launch_warp2_tma(const float* xb, const float* xa, const float* flow_hat, const float* flow_ab,
+                     const float* flow_ba, const float* tab_x, const float* tab_y, float* out, float* flows_out, int N,
+                     int H, int W, int h4, int w4, const WarpGeom& g, cudaStream_t st) {
+  using namespace wt;
+  static const int enabled = []() {
+    const char* e = getenv("B200VC_WARP_TMA");
+    return e ? atoi(e) : 1;
+  }();
+  if (!enabled || W % 4 != 0 || (int64_t)H * W < 128 * 128 || (int64_t)N * 3 >= (1 << 30) ||
+      ((reinterpret_cast<uintptr_t>(xb) | reinterpret_cast<uintptr_t>(xa)) & 15u) != 0)
+    return B200VC_EUNSUPPORTED;
+  CUtensorMap map_b, map_a;
+  if (!make_img_map(&map_b, xb, N, H, W) || !make_img_map(&map_a, xa, N, H, W)) return B200VC_EUNSUPPORTED;
+  static bool configured[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !configured[dev]) {
+    if (cudaFuncSetAttribute(warp2_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return B200VC_EUNSUPPORTED;
+    }
+    configured[dev] = true;
+  }
+  dim3 grid((W + kTW - 1) / kTW, (H + kTH - 1) / kTH, N);
+  warp2_tma_kernel<<<grid, kThreads, kSmemBytes, st>>>(map_b, map_a, xb, xa, flow_hat, flow_ab, flow_ba, tab_x, tab_y,
+                                                        out, flows_out, h4, w4, g);
+  return check_launch("warp2_lhbdc_f32(tma)");
 }
 
 }  // namespace b200vc
