@@ -316,6 +316,11 @@ def run_product(args):
             kernels[name] = {"launches": r["launches"], "ms_per_step": r["ms"] / steps,
                              "algorithmic_MB_per_step": r["bytes"] / steps / 1e6, "GBps": gbs,
                              "frac_of_peak": gbs / peak if gbs else None}
+            if "by_shape" in r:
+                kernels[name]["by_shape"] = {
+                    t: {"launches": v["launches"], "us_per_launch": 1e3 * v["ms"] / v["launches"],
+                        "GBps": v["bytes"] / (v["ms"] / 1e3) / 1e9 if v["ms"] > 0 else None}
+                    for t, v in r["by_shape"].items()}
         hot = {k: v for k, v in kernels.items() if k in HOT_KERNELS}
         dom = max(hot, key=lambda k: hot[k]["ms_per_step"]) if hot else None
         hot_ms = sum(v["ms_per_step"] for v in hot.values())

@@ -40,12 +40,18 @@ def profile_end():
     torch.cuda.synchronize()
     out = {}
     for name, items in rec.items():
-        ms = sum(s.elapsed_time(e) for s, e, _ in items)
-        out[name] = {"launches": len(items), "ms": ms, "bytes": float(sum(b for _, _, b in items))}
+        ms = sum(s.elapsed_time(e) for s, e, _, _ in items)
+        out[name] = {"launches": len(items), "ms": ms, "bytes": float(sum(b for _, _, b, _ in items))}
+        tags = sorted({t for _, _, _, t in items if t is not None})
+        if tags:
+            out[name]["by_shape"] = {
+                t: {"launches": sum(1 for i in items if i[3] == t),
+                    "ms": sum(i[0].elapsed_time(i[1]) for i in items if i[3] == t),
+                    "bytes": float(sum(i[2] for i in items if i[3] == t))} for t in tags}
     return out
 
 
-def _run(name, nbytes, call):
+def _run(name, nbytes, call, tag=None):
     """Launch one kernel through the C-ABI: count it, check the return code, optionally time it."""
     global _launches
     _launches += 1
@@ -56,7 +62,7 @@ def _run(name, nbytes, call):
         s.record()
         rc = call()
         e.record()
-        _prof.setdefault(name, []).append((s, e, nbytes))
+        _prof.setdefault(name, []).append((s, e, nbytes, tag))
     _lib.check(rc, name)
 
 
@@ -292,7 +298,7 @@ def gdn(x, params, inverse=False, addend=None, impl=0):
     nbytes = (2 + (addend is not None)) * C * 4 * N * H * W
     _run("gdn_f32", nbytes, lambda: lib.b200vc_gdn_f32(
         x.data_ptr(), params.data_ptr(), addend.data_ptr() if addend is not None else None, out.data_ptr(), N, C,
-        H * W, 1 if inverse else 0, impl, _stream()))
+        H * W, 1 if inverse else 0, impl, _stream()), tag=f"{N}x{C}x{H}x{W}")
     return out
 
 

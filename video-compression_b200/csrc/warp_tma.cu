@@ -397,9 +397,11 @@ int launch_warp2_tma(const float* xb, const float* xa, const float* flow_hat, co
                      const float* flow_ba, const float* tab_x, const float* tab_y, float* out, float* flows_out, int N,
                      int H, int W, int h4, int w4, const WarpGeom& g, cudaStream_t st) {
   using namespace wt;
+  // opt-in: on this pool's B200 the staged fused kernel measured no faster than the gather version on the bench's
+  // (rough, random-weight) flows (0.306 vs 0.294 ms/step); it is kept, bit-exact and tested, for smooth flows
   static const int enabled = []() {
-    const char* e = getenv("B200VC_WARP_TMA");
-    return e ? atoi(e) : 1;
+    const char* e = getenv("B200VC_WARP2_TMA");
+    return e ? atoi(e) : 0;
   }();
   if (!enabled || W % 4 != 0 || (int64_t)H * W < 128 * 128 || (int64_t)N * 3 >= (1 << 30) ||
       ((reinterpret_cast<uintptr_t>(xb) | reinterpret_cast<uintptr_t>(xa)) & 15u) != 0)
