@@ -148,3 +148,19 @@ def test_search_form_warp_blend_sse(shape):
     assert abs(sse.sum().item() / xc.numel() - mse) / mse < 1e-5
     sse2, none = ops.warp2_half_sse(x1 * 1.3 - 0.1, x2, f1, f2, xc, "ac1")
     assert none is None and torch.equal(sse, sse2)
+
+
+@pytest.mark.parametrize("env", [{"B200VC_WARP_TMA": "0", "B200VC_WARP2_TMA": "0"},
+                                 {"B200VC_WARP_TMA": "1", "B200VC_WARP2_TMA": "1"}])
+@pytest.mark.parametrize("size", [(256, 256), (272, 480)])
+def test_gather_and_tma_staged_kernels_agree_bit_for_bit(env, size):
+    """Both implementations of every warp (direct gather / TMA-staged taps) are bit-exact against the oracle on
+    smooth flows; the choice is read once per process, so each configuration runs in its own interpreter."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ, H=str(size[0]), W=str(size[1]), **env)
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "try_warp_tma.py")], env=e, capture_output=True,
+                       text=True, timeout=240)
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout + r.stderr
+    assert r.stdout.count("bit-exact 1.0") >= 3
