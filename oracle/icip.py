@@ -1,0 +1,44 @@
+"""TEST INFRASTRUCTURE (oracle).  Torch restatement of ICIP2024/src/opt_helpers.py:23-51 (prediction_flowonly,
+get_best_down_ratio_prediction), ICIP2024/src/model/m.py:71-82 (convert_scales) and ICIP2024/src/utils.py:273-283
+(MSE, PSNR).  The warp is ``oracle.warp.warp_ac1``, pinned bit for bit against the reference's own
+``FlowGuidedB.warp`` by oracle/make_golden.py."""
+import torch
+import torch.nn.functional as F
+
+from .warp import warp_ac1
+
+
+def convert_scales(scale1, scale2, x):
+    if not torch.is_tensor(scale1):
+        scale1 = torch.tensor([scale1])
+        scale2 = torch.tensor([scale2])
+    scale1 = scale1.view(-1, 1, 1, 1).to(x.device).float()
+    scale2 = scale2.view(-1, 1, 1, 1).to(x.device).float()
+    scale1 = torch.round(scale1 * 10 ** 2) / (10 ** 2)
+    scale2 = torch.round(scale2 * 10 ** 2) / (10 ** 2)
+    return scale1, scale2
+
+
+def prediction_flowonly(model, xcur, xref1, xref2, scale1, scale2, down_ratio):
+    scale1, scale2 = convert_scales(scale1, scale2, xref1)
+    f21, f12 = model.estimate_flow(xref1, xref2, down_ratio).chunk(2, 1)
+    f21 = F.interpolate(f21, scale_factor=2, mode="bilinear", align_corners=False) * 2
+    f12 = F.interpolate(f12, scale_factor=2, mode="bilinear", align_corners=False) * 2
+    f21 = f21 * scale1
+    f12 = f12 * scale2
+    wref1 = warp_ac1(xref1, f21)
+    wref2 = warp_ac1(xref2, f12)
+    mask = 0.5
+    return mask * wref1 + (1 - mask) * wref2
+
+
+def get_best_down_ratio_prediction(model, xref1, xref2, scale1, scale2, xcur, level=None, beta=None):
+    best_pred_psnr = 0
+    for down_ratio in [1, 2, 4, 8, 16]:
+        x_hat = prediction_flowonly(model, xcur, xref1, xref2, scale1, scale2, down_ratio)
+        mse = torch.mean((torch.clamp(x_hat, 0, 1) - xcur) ** 2)
+        psnr = 10 * torch.log10((1 ** 2) / mse)
+        if psnr > best_pred_psnr:
+            best_pred_psnr = psnr
+            best_down_ratio = down_ratio
+    return best_down_ratio, best_pred_psnr

@@ -164,3 +164,35 @@ def test_gather_and_tma_staged_kernels_agree_bit_for_bit(env, size):
                        text=True, timeout=240)
     assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout + r.stderr
     assert r.stdout.count("bit-exact 1.0") >= 3
+
+
+def test_warp_4k_frame():
+    """BASELINE config 5 geometry (OJSP2025: 3840x2160, align_corners=True warp): the largest single-plane size."""
+    from b200vc import ops
+    g = torch.Generator().manual_seed(2160)
+    img = torch.rand(1, 3, 2160, 3840, generator=g).cuda()
+    f = 6.0 * torch.randn(1, 2, 2160 // 8, 3840 // 8, generator=g)
+    flow = torch.nn.functional.interpolate(f, size=(2160, 3840), mode="bilinear", align_corners=False).cuda()
+    want = o_warp.warp_ac1(img, flow)
+    got = ops.backwarp(img, flow, "ac1")
+    assert torch.equal(got, want)
+    xc = torch.rand(1, 3, 2160, 3840, generator=g).cuda()
+    sse, _ = ops.warp2_half_sse(img, img.flip(3), flow, -flow, xc, "ac1")
+    pred = 0.5 * want + 0.5 * o_warp.warp_ac1(img.flip(3), -flow)
+    ref = ((pred.clamp(0, 1) - xc).double() ** 2).sum().item()
+    assert abs(sse.item() - ref) / ref < 1e-6
+
+
+def test_empty_batches_return_empty_results():
+    """Edge case the torch ops of the reference handle too: a zero-sized batch."""
+    from b200vc import modules, ops
+    e3 = torch.empty(0, 3, 16, 24, device="cuda")
+    e2 = torch.empty(0, 2, 16, 24, device="cuda")
+    assert ops.backwarp(e3, e2, "lhbdc").shape == (0, 3, 16, 24)
+    pred, res, sse = ops.blend_residual("half", None, e3, e3, e3, want_sse=True)
+    assert pred.shape == (0, 3, 16, 24) and sse.numel() == 0
+    e128 = torch.empty(0, 128, 4, 4, device="cuda")
+    r = ops.gauss_cond(e128, e128, e128)
+    assert r["y_hat"].shape == (0, 128, 4, 4) and r["bits"].numel() == 0
+    gdn = modules.GDN(128).cuda().eval()
+    assert gdn(e128).shape == (0, 128, 4, 4)

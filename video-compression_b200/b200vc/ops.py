@@ -135,6 +135,8 @@ def backwarp(img, flow, variant="lhbdc", out=None, arith=0):
         raise RuntimeError(f"backwarp: flow shape {tuple(flow.shape)} does not match image {tuple(img.shape)}")
     if out is None:
         out = torch.empty_like(img, memory_format=torch.contiguous_format)
+    if img.numel() == 0:  # empty batch: nothing to launch (the reference's grid_sample returns an empty tensor too)
+        return out
     o, op, obs = _planes(out, "backwarp(out)")
     if o is not out or tuple(out.shape) != (N, C, H, W):
         raise RuntimeError("backwarp: `out` must be a dense [N,C,H,W] block (channel slices are fine)")
@@ -166,6 +168,8 @@ def warp2_lhbdc(x_before, x_after, flow_hat, flow_ab, flow_ba, return_flows=Fals
     tx, ty = grid_tables("lhbdc", H, W, xb.device)
     out = torch.empty((N, 6, H, W), device=xb.device, dtype=torch.float32)
     flows = torch.empty((N, 4, H, W), device=xb.device, dtype=torch.float32) if return_flows else None
+    if N == 0:
+        return (out, flows) if return_flows else out
     lib = _lib.load()
     # algorithmic bytes: 2 references in, 6-channel concat out, quarter-res flows (4+2+2 channels over HW/16)
     nbytes = N * H * W * (12 * 4 + 8 * 4 / 16 + (16 if return_flows else 0))
@@ -230,6 +234,8 @@ def blend_residual(mode, mask, a, b, x_cur, want_pred=True, want_res=True, want_
         mp = mask.data_ptr()
     pred = torch.empty_like(x) if want_pred else None
     res = torch.empty_like(x) if want_res else None
+    if N == 0:
+        return pred, res, (torch.zeros(0, device=x.device, dtype=torch.float64) if want_sse else None)
     nb = reduce_blocks(H * W)
     part = torch.empty(N * nb, device=x.device, dtype=torch.float64) if want_sse else None
     lib = _lib.load()
@@ -294,6 +300,8 @@ def gdn(x, params, inverse=False, addend=None, impl=0):
     # residual form: accumulate into the addend's storage (the reference's `out += identity`); the tcgen05
     # kernel then needs no addend traffic inside the SM -- the result tile leaves through a TMA reduce-add
     out = addend if (addend is not None and _GDN_INPLACE_ADD) else torch.empty_like(x)
+    if x.numel() == 0:
+        return out
     lib = _lib.load()
     nbytes = (2 + (addend is not None)) * C * 4 * N * H * W
     _run("gdn_f32", nbytes, lambda: lib.b200vc_gdn_f32(
@@ -330,6 +338,9 @@ def gauss_cond(y, scales, means, scale_bound=0.11, lik_bound=1e-9, inv_gain=None
         inv_gain = _contig(inv_gain.reshape(-1), "gauss_cond(inv_gain)")
         if inv_gain.numel() != C:
             raise RuntimeError("gauss_cond: inv_gain must have C entries")
+    if y.numel() == 0:
+        return {"y_hat": y_hat, "lik": lik, "bits": torch.zeros(N, device=dev, dtype=torch.float64) if want_bits else None,
+                "symbols": sym, "indexes": idx}
     nb = reduce_blocks(C * H * W)
     part = torch.empty(N * nb, device=dev, dtype=torch.float64) if want_bits else None
     p = lambda t: t.data_ptr() if t is not None else None
@@ -374,6 +385,9 @@ def entropy_bottleneck(z, packed, lik_bound=1e-9, gain=None, inv_gain=None, want
             raise RuntimeError(f"entropy_bottleneck: {nm} must have C entries")
     gain = _contig(gain.reshape(-1), "eb(gain)") if gain is not None else None
     inv_gain = _contig(inv_gain.reshape(-1), "eb(inv_gain)") if inv_gain is not None else None
+    if z.numel() == 0:
+        return {"z_hat": z_hat, "lik": lik, "bits": torch.zeros(N, device=dev, dtype=torch.float64) if want_bits else None,
+                "symbols": sym}
     nb = reduce_blocks(4 * C * H * W)  # scalar kernel (heavy per-element math): one element per thread
     part = torch.empty(N * nb, device=dev, dtype=torch.float64) if want_bits else None
     p = lambda t: t.data_ptr() if t is not None else None
