@@ -140,6 +140,31 @@ def section_timing():
         with torch.no_grad():
             t_ref = timeit(lambda: torch.log(oe(z)[1]).sum())
         rec(f"entropy_bottleneck N={N}", timeit(lambda: ops.entropy_bottleneck(z, packed)), 12 * z.numel(), t_ref)
+    # rANS coder at the 1080p residual-latent shape [1,128,68,120] (1 044 480 symbols)
+    from b200vc import coding
+    gc = modules.GaussianConditional(None).cuda().eval()
+    gc.update_scale_table(modules.get_scale_table())
+    y, s_, m_ = gc_case(3, 1, 128, 68, 120)
+    idx = gc.build_indexes(s_)
+    sym = gc.quantize(y, "symbols", m_)
+    tab = modules.gc_tables(gc)
+    for sl in (4096, 1024, 256):
+        data = coding.rans_encode(sym, idx, tab, stream_len=sl)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            data = coding.rans_encode(sym, idx, tab, stream_len=sl)
+        te = (time.perf_counter() - t0) / 5
+        t0 = time.perf_counter()
+        for _ in range(5):
+            back = coding.rans_decode(data, idx, tab)
+        torch.cuda.synchronize()
+        td = (time.perf_counter() - t0) / 5
+        ok = bool((back.view_as(sym) == sym).all().item())
+        est = ops.gauss_cond(y, s_, m_, want_y_hat=False, want_lik=False)["bits"].item()
+        print(f"rans stream_len={sl:5d}: encode {te*1e3:7.2f} ms  decode {td*1e3:7.2f} ms (wall, incl. D2H/H2D + container) "
+              f"{len(data)} B = {8*len(data)/est:.4f} x estimated bits, round trip {ok}")
+        res[f"rans_{sl}"] = {"encode_ms": te * 1e3, "decode_ms": td * 1e3, "bytes": len(data), "ratio_to_estimate": 8 * len(data) / est}
     OUT["timing"] = res
 
 
