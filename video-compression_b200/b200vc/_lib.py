@@ -31,6 +31,7 @@ _SIGNATURES = {
     "b200vc_gdn_params_floats": (c_int64, [c_int]),
     "b200vc_gdn_prepare_f32": (c_int, [_fp, _fp, c_float, c_float, c_float, _fp, c_int, c_void_p]),
     "b200vc_gdn_f32": (c_int, [_fp, _fp, _fp, _fp, c_int, c_int, c_int64, c_int, c_int, c_void_p]),
+    "b200vc_debug_set_gdn_trace": (None, [_fp]),
     "b200vc_gauss_cond_f32": (c_int, [_fp, _fp, _fp, c_int64, _fp, _fp, _fp, _fp, _fp, _fp, c_int, c_float, c_float, _fp, c_int, c_int, c_int, c_int64, c_void_p]),
     "b200vc_eb_prepare_f32": (c_int, [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), _fp, _fp, c_int, c_void_p]),
     "b200vc_entropy_bottleneck_f32": (c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, c_float, _fp, c_int, c_int, c_int, c_int64, c_void_p]),

@@ -180,7 +180,12 @@ __global__ void __launch_bounds__(kThreads, 1)
 gdn_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_out,
               const __grid_constant__ CUtensorMap map_add, const float* __restrict__ params,
               const float* __restrict__ addend, int64_t HW, int tiles_per_sample, int total_tiles, int inverse,
-              int accumulate) {
+              int accumulate, long long* __restrict__ trace) {
+  // trace (diagnostics, normally null): CTA 0 stamps clock64() per tile and pipeline event, 8 slots per tile
+#define B200VC_TRACE(slot)                                                               \
+  do {                                                                                   \
+    if (trace != nullptr && blockIdx.x == 0 && k < 256) trace[k * 8 + (slot)] = clock64(); \
+  } while (0)
   // addend handling: accumulate != 0  => `out` already holds the addend (in-place residual add): the result
   //                                      tile leaves through a TMA reduce-add, no addend traffic in the SM;
   //                  addend != null   => the epilogue reads it from global (L2-prefetched by the producer).
@@ -265,6 +270,7 @@ gdn_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         const int row0 = (tile / tiles_per_sample) * kC;
         const int p0 = (tile % tiles_per_sample) * kTileP;
         mbar_wait(raw_empty(r), ph ^ 1);
+        B200VC_TRACE(0);  // load issued
         mbar_arrive_expect_tx(raw_full(r), kTileBytes);
         tma_load_2d(raw_addr(r), &map_x, p0, row0, raw_full(r));
         tma_load_2d(raw_addr(r) + kHalfBytes, &map_x, p0 + 32, row0, raw_full(r));
@@ -285,6 +291,7 @@ gdn_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         mbar_wait(d_empty(d), pd ^ 1);
         mbar_wait(ab_full(a), pa);
         tc_fence_after();
+        B200VC_TRACE(3);  // operands ready, MMA issue starts
         // Two accumulators: the tensor core's fp32 accumulation truncates, so the 32 small cross-term steps
         // go to their own accumulator and never disturb the 16-step main sum; the epilogue adds them (RN).
         const uint32_t d1 = tmem + kColD + kColDStage * d, d2 = d1 + kTileP;
@@ -309,10 +316,12 @@ gdn_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++k) {
       const int r = k % R, pr = (k / R) & 1, a = k % A, pa = (k / A) & 1;
       mbar_wait(raw_full(r), pr);
+      if (t == 0) B200VC_TRACE(1);  // raw tile landed
       const float4* raw4 = reinterpret_cast<const float4*>(smem_gen + CFG::kRawOff + r * kTileBytes);
       float4* hi4 = reinterpret_cast<float4*>(smem_gen + CFG::kAbOff + a * 2 * kTileBytes);
       float4* lo4 = hi4 + kTileBytes / 16;
       mbar_wait(ab_empty(a), pa ^ 1);
+      if (t == 0) B200VC_TRACE(2);  // operand slot free: split starts
 #pragma unroll
       for (int b0 = 0; b0 < kIters; b0 += 4) {
         float4 v[4];
@@ -349,6 +358,7 @@ gdn_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
       const int p0 = (tile % tiles_per_sample) * kTileP;
       mbar_wait(d_full(d), pd);
       tc_fence_after();
+      if (leader) B200VC_TRACE(4);  // accumulators complete: epilogue starts
       uint32_t v1[32], v2[32];
       const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + kColD + kColDStage * d + 32 * h;
       tmem_ld32(taddr, v1);
@@ -396,6 +406,7 @@ gdn_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
       fence_proxy_async();  // result tile (generic writes) -> visible to the TMA store
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (leader) {
+        B200VC_TRACE(5);  // epilogue math done, store issued
         if (accumulate) {
           tma_reduce_add_2d(&map_out, raw_addr(r), p0, row0);
           if ((int64_t)p0 + 32 < HW) tma_reduce_add_2d(&map_out, raw_addr(r) + kHalfBytes, p0 + 32, row0);
@@ -410,6 +421,7 @@ gdn_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
           asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           mbar_arrive(raw_empty((k - 1) % R));
         }
+        B200VC_TRACE(6);  // previous tile's slot released
       }
     }
     if (leader && k > 0) {
@@ -456,6 +468,8 @@ static bool make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t 
   return r == CUDA_SUCCESS;
 }
 
+long long* g_trace = nullptr;  // set through b200vc_debug_set_gdn_trace (diagnostics only)
+
 template <class CFG>
 static int launch_cfg(const CUtensorMap& map_x, const CUtensorMap& map_out, const CUtensorMap& map_add,
                       const float* params, const float* addend, int64_t HW, int tps, int total, int inverse,
@@ -473,7 +487,7 @@ static int launch_cfg(const CUtensorMap& map_x, const CUtensorMap& map_out, cons
     configured[dev] = true;
   }
   gdn_tc_kernel<CFG><<<grid, kThreads, CFG::kSmemBytes, st>>>(map_x, map_out, map_add, params, addend, HW, tps, total,
-                                                              inverse, accumulate);
+                                                              inverse, accumulate, g_trace);
   return check_launch("gdn_f32(tcgen05)");
 }
 
@@ -518,3 +532,7 @@ int launch_gdn_tc(const float* x, const float* params, const float* addend, floa
 }
 
 }  // namespace b200vc
+
+// Diagnostics: device buffer of 256 x 8 clock64() stamps written by CTA 0 of the next tcgen05 GDN launches
+// (slots: 0 load issued, 1 raw landed, 2 split starts, 3 MMA issue, 4 epilogue starts, 5 store issued, 6 slot released).
+extern "C" void b200vc_debug_set_gdn_trace(long long* device_buffer) { b200vc::tc::g_trace = device_buffer; }
