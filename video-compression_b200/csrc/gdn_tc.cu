@@ -51,7 +51,7 @@ struct Cfg {
   static constexpr int kRawOff = 0;
   static constexpr int kAbOff = R * kTileBytes;              // A x (hi | lo)
   static constexpr int kBarOff = kAbOff + A * 2 * kTileBytes;
-  static constexpr int kNumBars = 2 * R + 2 * A + 5;
+  static constexpr int kNumBars = 2 * R + 4 * A + 5;
   static constexpr int kSmemBytes = kBarOff + 8 * kNumBars + 16 + 1024 /*alignment slack*/;
 };
 
@@ -140,6 +140,12 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
       ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(kIdesc), "r"(accumulate)
       : "memory");
 }
+// one lane of a converged warp (elect.sync): keeps the guarded code's operands in uniform registers
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -156,6 +162,38 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// issue only; pair with tmem_ld_wait() before the registers are read
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,"
+      "%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// norms are positive normal numbers (beta >= 2^-18 ... reparametrisation bound): the raw MUFU approximations
+// (max relative error 2^-22 / 2^-23) need none of sqrtf()/rsqrtf()'s range fix-ups or slow-path branches
+__device__ __forceinline__ float rsqrt_approx(float v) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ float sqrt_approx(float v) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
 }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
   asm volatile(
@@ -175,16 +213,16 @@ __device__ __forceinline__ float to_tf32_rna(float v) {
 }
 
 // params layout (gdn.cu): [0,C) beta | gamma | gammaT | hi[i][j] (C*C) | lo[i][j] (C*C)
-template <class CFG>
+template <class CFG, int INV>
 __global__ void __launch_bounds__(kThreads, 1)
 gdn_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_out,
               const __grid_constant__ CUtensorMap map_add, const float* __restrict__ params,
-              const float* __restrict__ addend, int64_t HW, int tiles_per_sample, int total_tiles, int inverse,
-              int accumulate, long long* __restrict__ trace) {
-  // trace (diagnostics, normally null): CTA 0 stamps clock64() per tile and pipeline event, 8 slots per tile
+              const float* __restrict__ addend, int64_t HW, int tiles_per_sample, int total_tiles, int accumulate,
+              long long* __restrict__ trace) {
+  // trace (diagnostics, normally null): CTA 0 stamps clock64() per tile and pipeline event, 16 slots per tile
 #define B200VC_TRACE(slot)                                                               \
   do {                                                                                   \
-    if (trace != nullptr && blockIdx.x == 0 && k < 256) trace[k * 8 + (slot)] = clock64(); \
+    if (trace != nullptr && blockIdx.x == 0 && k < 256) trace[k * 16 + (slot)] = clock64(); \
   } while (0)
   // addend handling: accumulate != 0  => `out` already holds the addend (in-place residual add): the result
   //                                      tile leaves through a TMA reduce-add, no addend traffic in the SM;
@@ -199,11 +237,13 @@ gdn_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
   const uint32_t bar_base = smem_base + CFG::kBarOff;
   auto raw_full = [&](int r) { return bar_base + 8 * r; };
   auto raw_empty = [&](int r) { return bar_base + 8 * (R + r); };
-  auto ab_full = [&](int a) { return bar_base + 8 * (2 * R + a); };
-  auto ab_empty = [&](int a) { return bar_base + 8 * (2 * R + A + a); };
-  auto d_full = [&](int d) { return bar_base + 8 * (2 * R + 2 * A + d); };
-  auto d_empty = [&](int d) { return bar_base + 8 * (2 * R + 2 * A + 2 + d); };
-  const uint32_t gamma_ready = bar_base + 8 * (2 * R + 2 * A + 4);
+  // operand barriers exist per channel half (c = 0: channels 0-63 = k-steps 0-7, c = 1: the rest), so that the split
+  // of tile k+1 overlaps the second half of tile k's MMAs although there is a single operand stage
+  auto ab_full = [&](int a, int c) { return bar_base + 8 * (2 * R + 2 * a + c); };
+  auto ab_empty = [&](int a, int c) { return bar_base + 8 * (2 * R + 2 * A + 2 * a + c); };
+  auto d_full = [&](int d) { return bar_base + 8 * (2 * R + 4 * A + d); };
+  auto d_empty = [&](int d) { return bar_base + 8 * (2 * R + 4 * A + 2 + d); };
+  const uint32_t gamma_ready = bar_base + 8 * (2 * R + 4 * A + 4);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + CFG::kBarOff + 8 * CFG::kNumBars);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -213,10 +253,11 @@ gdn_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
       mbar_init(raw_full(r), 1);
       mbar_init(raw_empty(r), 1);
     }
-    for (int a = 0; a < A; ++a) {
-      mbar_init(ab_full(a), kXfWarps);   // one arrival per warp (lane 0 after __syncwarp)
-      mbar_init(ab_empty(a), 1);
-    }
+    for (int a = 0; a < A; ++a)
+      for (int c = 0; c < 2; ++c) {
+        mbar_init(ab_full(a, c), kXfWarps);   // one arrival per warp (lane 0 after __syncwarp)
+        mbar_init(ab_empty(a, c), 1);
+      }
     for (int d = 0; d < 2; ++d) {
       mbar_init(d_full(d), 1);
       mbar_init(d_empty(d), kEpiWarps);
@@ -282,30 +323,45 @@ gdn_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      mbar_wait(gamma_ready, 0);
-      tc_fence_after();
-      int k = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++k) {
-        const int a = k % A, pa = (k / A) & 1, d = k & 1, pd = (k >> 1) & 1;
-        mbar_wait(d_empty(d), pd ^ 1);
-        mbar_wait(ab_full(a), pa);
+    // The whole warp runs the loop with warp-uniform values (the TMEM base goes through a shuffle so that ptxas
+    // knows it is uniform) and one elected lane issues.  Written as `if (lane == 0) { loop }` the operands live in
+    // per-thread registers and ptxas wraps EVERY tcgen05.mma in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall
+    // loop, which costs more than the MMA itself (tools/mma_bench.cu).
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+    mbar_wait(gamma_ready, 0);
+    tc_fence_after();
+    int k = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++k) {
+      const int a = k % A, pa = (k / A) & 1, d = k & 1, pd = (k >> 1) & 1;
+      mbar_wait(d_empty(d), pd ^ 1);
+      if (lane == 0) B200VC_TRACE(14);  // accumulator stage free
+      // Two accumulators: the tensor core's fp32 accumulation truncates, so the 32 small cross-term steps
+      // go to their own accumulator and never disturb the 16-step main sum; the epilogue adds them (RN).
+      const uint32_t d1 = tmem_u + kColD + kColDStage * d, d2 = d1 + kTileP;
+      const uint64_t hi_desc = make_b_desc(hi_addr(a)), lo_desc = make_b_desc(lo_addr(a));
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        mbar_wait(ab_full(a, c), pa);
         tc_fence_after();
-        B200VC_TRACE(3);  // operands ready, MMA issue starts
-        // Two accumulators: the tensor core's fp32 accumulation truncates, so the 32 small cross-term steps
-        // go to their own accumulator and never disturb the 16-step main sum; the epilogue adds them (RN).
-        const uint32_t d1 = tmem + kColD + kColDStage * d, d2 = d1 + kTileP;
+        if (elect_one()) {
+          if (c == 0) B200VC_TRACE(3);  // operands ready, MMA issue starts
+          // descriptor start address advances 1024 B (8 channel rows) per k-step
 #pragma unroll
-        for (int g = 0; g < kC / 8; ++g)   // D1  = ghi * hi
-          umma_tf32_ts(d1, tmem + kColGhi + 8 * g, make_b_desc(hi_addr(a) + g * 1024), g != 0 ? 1u : 0u);
+          for (int g = 8 * c; g < 8 * c + 8; ++g)   // D1 += ghi * hi
+            umma_tf32_ts(d1, tmem_u + kColGhi + 8 * g, hi_desc + (uint64_t)(g * (1024 >> 4)), g != 0 ? 1u : 0u);
 #pragma unroll
-        for (int g = 0; g < kC / 8; ++g)   // D2  = ghi * lo
-          umma_tf32_ts(d2, tmem + kColGhi + 8 * g, make_b_desc(lo_addr(a) + g * 1024), g != 0 ? 1u : 0u);
+          for (int g = 8 * c; g < 8 * c + 8; ++g)   // D2 += ghi * lo
+            umma_tf32_ts(d2, tmem_u + kColGhi + 8 * g, lo_desc + (uint64_t)(g * (1024 >> 4)), g != 0 ? 1u : 0u);
 #pragma unroll
-        for (int g = 0; g < kC / 8; ++g)   // D2 += glo * hi
-          umma_tf32_ts(d2, tmem + kColGlo + 8 * g, make_b_desc(hi_addr(a) + g * 1024), 1u);
-        umma_commit(ab_empty(a));  // operand pair consumed
-        umma_commit(d_full(d));    // accumulators ready
+          for (int g = 8 * c; g < 8 * c + 8; ++g)   // D2 += glo * hi
+            umma_tf32_ts(d2, tmem_u + kColGlo + 8 * g, hi_desc + (uint64_t)(g * (1024 >> 4)), 1u);
+          umma_commit(ab_empty(a, c));  // this half of the operand pair is consumed
+          if (c == 1) {
+            umma_commit(d_full(d));     // accumulators ready
+            B200VC_TRACE(15);           // all MMAs of the tile issued
+          }
+        }
+        __syncwarp();
       }
     }
   } else if (warp < kFirstEpi) {
@@ -320,28 +376,36 @@ gdn_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
       const float4* raw4 = reinterpret_cast<const float4*>(smem_gen + CFG::kRawOff + r * kTileBytes);
       float4* hi4 = reinterpret_cast<float4*>(smem_gen + CFG::kAbOff + a * 2 * kTileBytes);
       float4* lo4 = hi4 + kTileBytes / 16;
-      mbar_wait(ab_empty(a), pa ^ 1);
-      if (t == 0) B200VC_TRACE(2);  // operand slot free: split starts
 #pragma unroll
-      for (int b0 = 0; b0 < kIters; b0 += 4) {
-        float4 v[4];
+      for (int c = 0; c < 2; ++c) {
+        mbar_wait(ab_empty(a, c), pa ^ 1);
+        if (t == 0 && c == 0) B200VC_TRACE(2);  // operand slot free: split starts
+        // channel half c: rows 64c..64c+63 of both 32-position atoms = 2 x 512 float4
+        float4 v[kIters / 2];
 #pragma unroll
-        for (int it = 0; it < 4; ++it) v[it] = raw4[(b0 + it) * (kXfWarps * 32) + t];  // 4 loads in flight
+        for (int it = 0; it < kIters / 2; ++it) {
+          const int idx = it * (kXfWarps * 32) + t;            // 0..1023
+          v[it] = raw4[(idx >> 9) * 1024 + c * 512 + (idx & 511)];   // all loads in flight
+        }
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
+        for (int it = 0; it < kIters / 2; ++it) {
+          const int idx = it * (kXfWarps * 32) + t;
+          const int o = (idx >> 9) * 1024 + c * 512 + (idx & 511);
           float4 sq, hh, ll;
           sq.x = __fmul_rn(v[it].x, v[it].x); sq.y = __fmul_rn(v[it].y, v[it].y);
           sq.z = __fmul_rn(v[it].z, v[it].z); sq.w = __fmul_rn(v[it].w, v[it].w);
           hh.x = to_tf32_rna(sq.x); hh.y = to_tf32_rna(sq.y); hh.z = to_tf32_rna(sq.z); hh.w = to_tf32_rna(sq.w);
           ll.x = __fsub_rn(sq.x, hh.x); ll.y = __fsub_rn(sq.y, hh.y);
           ll.z = __fsub_rn(sq.z, hh.z); ll.w = __fsub_rn(sq.w, hh.w);
-          hi4[(b0 + it) * (kXfWarps * 32) + t] = hh;
-          lo4[(b0 + it) * (kXfWarps * 32) + t] = ll;
+          hi4[o] = hh;
+          lo4[o] = ll;
         }
+        if (t == 0 && c == 1) B200VC_TRACE(12);  // split stores issued
+        fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (t == 0 && c == 1) B200VC_TRACE(13);  // fence done
+        if (lane == 0) mbar_arrive(ab_full(a, c));
       }
-      fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
-      __syncwarp();
-      if (lane == 0) mbar_arrive(ab_full(a));
     }
   } else {
     // ------------------------------------------------------------------ epilogue (8 warps)
@@ -356,54 +420,67 @@ gdn_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
       const int r = k % R, d = k & 1, pd = (k >> 1) & 1;
       const int row0 = (tile / tiles_per_sample) * kC;
       const int p0 = (tile % tiles_per_sample) * kTileP;
+      // The x row segment is fetched before the accumulators are awaited (the raw tile landed long ago), so the
+      // shared-memory latency hides behind the d_full wait.  Logical 16-byte chunk cc of row i lives at 32-byte
+      // chunk ((cc >> 1) ^ (i & 3)), same 16-byte half; lanes with `flip` take the odd chunk of each pair first
+      // => the 8 rows of a quarter-warp hit 8 distinct 16-byte bank groups (conflict-free LDS.128 / STS.128).
+      float4* raw4 = reinterpret_cast<float4*>(smem_gen + CFG::kRawOff + r * kTileBytes) + h * (kHalfBytes / 16) + i * 8;
+      mbar_wait(raw_full(r), (k / R) & 1);
+      float4 xv[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int cc = c ^ (int)flip;
+        xv[c] = raw4[(((cc >> 1) ^ (i & 3)) << 1) | (cc & 1)];
+      }
       mbar_wait(d_full(d), pd);
       tc_fence_after();
       if (leader) B200VC_TRACE(4);  // accumulators complete: epilogue starts
-      uint32_t v1[32], v2[32];
+      // The accumulators come in four 8-column pieces (D1 and D2 each), the next piece loading while the current
+      // one is finished: with the 32 registers of x this stays inside the 96-register budget of a 576-thread CTA.
       const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + kColD + kColDStage * d + 32 * h;
-      tmem_ld32(taddr, v1);
-      tmem_ld32(taddr + kTileP, v2);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(d_empty(d));  // accumulators drained: the MMA warp may start tile k+2
-      float4* raw4 = reinterpret_cast<float4*>(smem_gen + CFG::kRawOff + r * kTileBytes) + h * (kHalfBytes / 16) + i * 8;
       const float* arow = addend ? addend + ((int64_t)row0 + i) * HW + p0 + 32 * h : nullptr;
       const int64_t pbase = (int64_t)p0 + 32 * h;
-      // logical 16-byte chunk cc of row i lives at 32-byte chunk ((cc >> 1) ^ (i & 3)), same 16-byte half;
-      // lanes with `flip` take the odd chunk of each pair first => the 8 rows of a quarter-warp hit 8 distinct
-      // 16-byte bank groups (conflict-free LDS.128 / STS.128).  All loads are issued before any store.
+      uint32_t v1[2][8], v2[2][8];
+      tmem_ld8_issue(taddr, v1[0]);
+      tmem_ld8_issue(taddr + kTileP, v2[0]);
 #pragma unroll
-      for (int c0 = 0; c0 < 8; c0 += 4) {
-        float4 xv[4], av[4];
-#pragma unroll
-        for (int c = c0; c < c0 + 4; ++c) {
-          const int cc = c ^ (int)flip;
-          xv[c - c0] = raw4[(((cc >> 1) ^ (i & 3)) << 1) | (cc & 1)];
-          av[c - c0] = (arow != nullptr && pbase + 4 * cc < HW) ? *reinterpret_cast<const float4*>(arow + 4 * cc)
-                                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int pc = 0; pc < 4; ++pc) {
+        tmem_ld_wait();
+        if (pc == 0 && leader) B200VC_TRACE(8);  // first accumulators in registers
+        if (pc < 3) {
+          tmem_ld8_issue(taddr + 8 * (pc + 1), v1[(pc + 1) & 1]);
+          tmem_ld8_issue(taddr + kTileP + 8 * (pc + 1), v2[(pc + 1) & 1]);
+        } else {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(d_empty(d));  // accumulators drained: the MMA warp may start tile k+2
         }
+        float nr[8];
 #pragma unroll
-        for (int c = c0; c < c0 + 4; ++c) {
+        for (int j = 0; j < 8; ++j)
+          nr[j] = __fadd_rn(__fadd_rn(__uint_as_float(v1[pc & 1][j]), __uint_as_float(v2[pc & 1][j])), beta);
+#pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2) {
+          const int c = 2 * pc + c2;
           const int cc = c ^ (int)flip;
+          const float xe[4] = {xv[c].x, xv[c].y, xv[c].z, xv[c].w};
           float o[4];
-          const float xe[4] = {xv[c - c0].x, xv[c - c0].y, xv[c - c0].z, xv[c - c0].w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const uint32_t u1 = flip ? v1[4 * (c ^ 1) + e] : v1[4 * c + e];
-            const uint32_t u2 = flip ? v2[4 * (c ^ 1) + e] : v2[4 * c + e];
-            const float acc = __fadd_rn(__uint_as_float(u1), __uint_as_float(u2));
-            const float nr = __fadd_rn(acc, beta);
-            o[e] = inverse == 2 ? nr : __fmul_rn(xe[e], inverse ? sqrtf(nr) : rsqrtf(nr));
+            const float n = flip ? nr[4 * (c2 ^ 1) + e] : nr[4 * c2 + e];
+            o[e] = INV == 2 ? n : __fmul_rn(xe[e], INV ? sqrt_approx(n) : rsqrt_approx(n));
           }
-          if (arow != nullptr) {
-            const float4 a4 = av[c - c0];
+          if (arow != nullptr && pbase + 4 * cc < HW) {
+            const float4 a4 = *reinterpret_cast<const float4*>(arow + 4 * cc);
             o[0] = __fadd_rn(o[0], a4.x); o[1] = __fadd_rn(o[1], a4.y);
             o[2] = __fadd_rn(o[2], a4.z); o[3] = __fadd_rn(o[3], a4.w);
           }
           raw4[(((cc >> 1) ^ (i & 3)) << 1) | (cc & 1)] = make_float4(o[0], o[1], o[2], o[3]);
         }
       }
+      if (leader) B200VC_TRACE(9);  // result written to the raw slot
       fence_proxy_async();  // result tile (generic writes) -> visible to the TMA store
+      if (leader) B200VC_TRACE(10);
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (leader) {
         B200VC_TRACE(5);  // epilogue math done, store issued
@@ -470,25 +547,37 @@ static bool make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t 
 
 long long* g_trace = nullptr;  // set through b200vc_debug_set_gdn_trace (diagnostics only)
 
-template <class CFG>
-static int launch_cfg(const CUtensorMap& map_x, const CUtensorMap& map_out, const CUtensorMap& map_add,
-                      const float* params, const float* addend, int64_t HW, int tps, int total, int inverse,
-                      int accumulate, int grid, cudaStream_t st) {
+template <class CFG, int INV>
+static int launch_inv(const CUtensorMap& map_x, const CUtensorMap& map_out, const CUtensorMap& map_add,
+                      const float* params, const float* addend, int64_t HW, int tps, int total, int accumulate,
+                      int grid, cudaStream_t st) {
   static bool configured[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !configured[dev]) {
-    if (cudaFuncSetAttribute(gdn_tc_kernel<CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::kSmemBytes) !=
-        cudaSuccess) {
+    if (cudaFuncSetAttribute(gdn_tc_kernel<CFG, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             CFG::kSmemBytes) != cudaSuccess) {
       set_error("gdn_f32: cannot reserve %d B of shared memory", CFG::kSmemBytes);
       (void)cudaGetLastError();
       return B200VC_EUNSUPPORTED;
     }
     configured[dev] = true;
   }
-  gdn_tc_kernel<CFG><<<grid, kThreads, CFG::kSmemBytes, st>>>(map_x, map_out, map_add, params, addend, HW, tps, total,
-                                                              inverse, accumulate, g_trace);
+  gdn_tc_kernel<CFG, INV><<<grid, kThreads, CFG::kSmemBytes, st>>>(map_x, map_out, map_add, params, addend, HW, tps,
+                                                                   total, accumulate, g_trace);
   return check_launch("gdn_f32(tcgen05)");
+}
+
+// inverse: 0 = GDN (x * rsqrt(norm)), 1 = IGDN (x * sqrt(norm)), 2 = norm only (debug)
+template <class CFG>
+static int launch_cfg(const CUtensorMap& map_x, const CUtensorMap& map_out, const CUtensorMap& map_add,
+                      const float* params, const float* addend, int64_t HW, int tps, int total, int inverse,
+                      int accumulate, int grid, cudaStream_t st) {
+  switch (inverse) {
+    case 0: return launch_inv<CFG, 0>(map_x, map_out, map_add, params, addend, HW, tps, total, accumulate, grid, st);
+    case 1: return launch_inv<CFG, 1>(map_x, map_out, map_add, params, addend, HW, tps, total, accumulate, grid, st);
+    default: return launch_inv<CFG, 2>(map_x, map_out, map_add, params, addend, HW, tps, total, accumulate, grid, st);
+  }
 }
 
 }  // namespace tc
@@ -521,7 +610,7 @@ int launch_gdn_tc(const float* x, const float* params, const float* addend, floa
     return e ? atoi(e) : 0;
   }();
   switch (cfg) {
-    // measured on B200 at [4,128,544,960]: <5,1> 4178 GB/s, <4,1> 4072 GB/s, <3,2> 3017 GB/s (raw-ring depth wins)
+    // raw-ring depth wins: <5,1> is the default; the other two stay for experiments (B200VC_GDN_TC_CFG)
     case 1: return launch_cfg<Cfg<3, 2>>(map_x, map_out, map_add, params, addend, HW, (int)tps, (int)total, inverse,
                                           accumulate, grid, st);
     case 2: return launch_cfg<Cfg<4, 1>>(map_x, map_out, map_add, params, addend, HW, (int)tps, (int)total, inverse,
@@ -533,6 +622,6 @@ int launch_gdn_tc(const float* x, const float* params, const float* addend, floa
 
 }  // namespace b200vc
 
-// Diagnostics: device buffer of 256 x 8 clock64() stamps written by CTA 0 of the next tcgen05 GDN launches
+// Diagnostics: device buffer of 256 x 16 clock64() stamps written by CTA 0 of the next tcgen05 GDN launches
 // (slots: 0 load issued, 1 raw landed, 2 split starts, 3 MMA issue, 4 epilogue starts, 5 store issued, 6 slot released).
 extern "C" void b200vc_debug_set_gdn_trace(long long* device_buffer) { b200vc::tc::g_trace = device_buffer; }
