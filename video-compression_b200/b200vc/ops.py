@@ -147,7 +147,8 @@ def backwarp(img, flow, variant="lhbdc", out=None, arith=0):
     lib = _lib.load()
     _run("warp_f32", (2 * C + 2) * 4 * N * H * W, lambda: lib.b200vc_warp_f32(
         ip, ibs, flow.data_ptr(), tx.data_ptr() if tx is not None else None,
-        ty.data_ptr() if ty is not None else None, op, obs, N, C, H, W, _VARIANTS[variant], arith, _stream()))
+        ty.data_ptr() if ty is not None else None, op, obs, N, C, H, W, _VARIANTS[variant], arith, _stream()),
+         tag=f"{N}x{C}x{H}x{W}")
     return out
 
 
