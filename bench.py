@@ -31,7 +31,7 @@ import torch  # noqa: E402
 METRIC = "1080p B-frames/s encode+decode (LHBDC hierarchical GOP-8)"
 UNIT = "B-frames/s"
 HOT_KERNELS = ("gdn_f32", "warp_f32", "warp2_lhbdc_f32", "blend_residual_f32", "gauss_cond_f32",
-               "entropy_bottleneck_f32")
+               "entropy_bottleneck_f32", "spynet_level_f32", "spynet_pyramid_f32")
 
 
 def parse():

@@ -107,6 +107,25 @@ B200VC_API int b200vc_warp2_half_sse_f32(const float* x1, const float* x2, const
                                          const float* x_cur, const float* tab_x, const float* tab_y, float* pred,
                                          double* partials, int N, int H, int W, int variant, void* stream);
 
+/* ------------------------------------------------------------------------------ SPyNet glue
+ * Replaces the non-convolutional part of Network.forward (LHBDC/model/flow.py:78-101).
+ *
+ * spynet_pyramid: Preprocess (flow.py:39-44: channel order reversed, (x - mean) / std) when `preprocess` != 0, then
+ *   `n_levels` (0..5) avg_pool2d(2, 2, count_include_pad=False) poolings (flow.py:83-88) in one pass.
+ *   frame [N,3,H,W] (batch stride frame_bs); levels = HOST array of n_levels + 1 device pointers, levels[l] =
+ *   [N,3,H>>l,W>>l] contiguous (floor division per level, as avg_pool2d); levels[0] is written only when
+ *   `preprocess` != 0 (otherwise the frame itself is level 0 and levels[0] may be NULL).
+ * spynet_level: one pyramid level's conv input (flow.py:93-98)
+ *   feat [N,8,H,W] = cat(first, backwarp(second, up), up),
+ *   up = interpolate(flow_prev [N,2,hp,wp], scale_factor=2, bilinear, align_corners=True) * 2.0, replicate-padded by
+ *   one row / column when H == 2*hp + 1 / W == 2*wp + 1.  flow_prev == NULL means the all-zero initial flow.
+ *   tab_x / tab_y as for warp_f32 (WARP_LHBDC). */
+B200VC_API int b200vc_spynet_pyramid_f32(const float* frame, int64_t frame_bs, float* const* levels, int N, int H,
+                                         int W, int n_levels, int preprocess, void* stream);
+B200VC_API int b200vc_spynet_level_f32(const float* first, int64_t first_bs, const float* second, int64_t second_bs,
+                                       const float* flow_prev, const float* tab_x, const float* tab_y, float* feat,
+                                       int N, int H, int W, int hp, int wp, void* stream);
+
 /* ------------------------------------------------------------------------------------ blend / residual
  * Replaces LHBDC/model/m.py:63-67, Flex-Rate.../b_model/b_model.py:68-73, ICIP2024/src/opt_helpers.py:35-45.
  *   a, b: the two warped references [N,3,H,W] (batch strides a_bs, b_bs: may be halves of the concat

@@ -50,24 +50,13 @@ class Network(nn.Module):
         self.netBasic = nn.ModuleList(_Basic() for _ in range(6))
 
     def forward(self, tenFirst, tenSecond):
-        pyr1, pyr2 = [self.netPreprocess(tenFirst)], [self.netPreprocess(tenSecond)]
-        for _ in range(5):
-            if pyr1[0].shape[2] > 32 or pyr1[0].shape[3] > 32:
-                pyr1.insert(0, F.avg_pool2d(pyr1[0], kernel_size=2, stride=2, count_include_pad=False))
-                pyr2.insert(0, F.avg_pool2d(pyr2[0], kernel_size=2, stride=2, count_include_pad=False))
-        top = pyr1[0]
-        flow = top.new_zeros([top.shape[0], 2, top.shape[2] // 2, top.shape[3] // 2])
+        # flow.py:78-101.  Preprocess + avg-pool pyramid: one launch per image (K-SPYPYR); per level the x2 flow
+        # upsample, replicate pad, warp and 8-channel concat: one launch (K-SPYLEVEL).  Convolutions stay on cuDNN.
+        pyr1, pyr2 = ops.spynet_pyramid(tenFirst), ops.spynet_pyramid(tenSecond)
+        flow = None  # the reference starts from new_zeros([N, 2, h // 2, w // 2]) (flow.py:90)
         for lvl, (a, b) in enumerate(zip(pyr1, pyr2)):
-            up = F.interpolate(flow, scale_factor=2, mode="bilinear", align_corners=True) * 2.0
-            if up.shape[2] != a.shape[2]:
-                up = F.pad(up, [0, 0, 0, 1], mode="replicate")
-            if up.shape[3] != a.shape[3]:
-                up = F.pad(up, [0, 1, 0, 0], mode="replicate")
-            feat = torch.empty((a.shape[0], 8, a.shape[2], a.shape[3]), device=a.device, dtype=a.dtype)
-            feat[:, 0:3] = a
-            ops.backwarp(b, up, "lhbdc", out=feat[:, 3:6])  # warp straight into the concat buffer
-            feat[:, 6:8] = up
-            flow = self.netBasic[lvl](feat) + up
+            feat = ops.spynet_level(a, b, flow)
+            flow = self.netBasic[lvl](feat) + feat[:, 6:8]
         return flow
 
 

@@ -152,6 +152,59 @@ def backwarp(img, flow, variant="lhbdc", out=None, arith=0):
     return out
 
 
+def spynet_pyramid(frame, preprocess=True, max_poolings=5):
+    """LHBDC/model/flow.py:80-88 in one launch: Preprocess (channel flip + ImageNet statistics) and the avg-pool
+    pyramid.  Returns the levels coarsest first, as the reference's ``tenFirst`` list ends up."""
+    import ctypes
+    frame, fp, fbs = _planes(frame, "spynet_pyramid(frame)")
+    N, C, H, W = frame.shape
+    if C != 3:
+        raise RuntimeError(f"spynet_pyramid: expected 3 channels, got {C}")
+    sizes = [(H, W)]
+    for _ in range(max_poolings):  # flow.py:84: pool while a side is larger than 32
+        h, w = sizes[-1]
+        if h > 32 or w > 32:
+            sizes.append((h // 2, w // 2))
+    n_levels = len(sizes) - 1
+    if not preprocess and n_levels == 0:
+        return [frame]
+    levels = [torch.empty((N, 3, h, w), device=frame.device, dtype=frame.dtype) if (l > 0 or preprocess) else frame
+              for l, (h, w) in enumerate(sizes)]
+    ptrs = (ctypes.c_void_p * (n_levels + 1))(*[(t.data_ptr() if (l > 0 or preprocess) else None)
+                                                for l, t in enumerate(levels)])
+    lib = _lib.load()
+    total = sum(h * w for h, w in sizes[1:]) + (H * W if preprocess else 0)
+    _run("spynet_pyramid_f32", 4 * 3 * N * (H * W + total), lambda: lib.b200vc_spynet_pyramid_f32(
+        fp, fbs, ptrs, N, H, W, n_levels, int(bool(preprocess)), _stream()))
+    return levels[::-1]
+
+
+def spynet_level(first, second, flow_prev=None):
+    """One SPyNet level's 8-channel conv input (flow.py:93-98): cat(first, backwarp(second, up), up) with
+    up = 2 * bilinear x2 (align_corners=True) of ``flow_prev``, replicate-padded to the level's size.
+    ``flow_prev=None`` is the all-zero initial flow."""
+    first, p1, bs1 = _planes(first, "spynet_level(first)")
+    second, p2, bs2 = _planes(second, "spynet_level(second)")
+    N, C, H, W = first.shape
+    if C != 3 or tuple(second.shape) != (N, 3, H, W):
+        raise RuntimeError(f"spynet_level: expected two [N,3,H,W] images, got {tuple(first.shape)} and {tuple(second.shape)}")
+    hp = wp = 0
+    if flow_prev is not None:
+        flow_prev = _contig(flow_prev, "spynet_level(flow_prev)")
+        if flow_prev.dim() != 4 or flow_prev.shape[0] != N or flow_prev.shape[1] != 2:
+            raise RuntimeError(f"spynet_level: flow_prev must be [N,2,h,w], got {tuple(flow_prev.shape)}")
+        hp, wp = flow_prev.shape[2:]
+        if H not in (2 * hp, 2 * hp + 1) or W not in (2 * wp, 2 * wp + 1):
+            raise RuntimeError(f"spynet_level: a {hp}x{wp} flow does not upsample to {H}x{W}")
+    tx, ty = grid_tables("lhbdc", H, W, first.device)
+    feat = torch.empty((N, 8, H, W), device=first.device, dtype=first.dtype)
+    lib = _lib.load()
+    _run("spynet_level_f32", 4 * N * (14 * H * W + 2 * hp * wp), lambda: lib.b200vc_spynet_level_f32(
+        p1, bs1, p2, bs2, flow_prev.data_ptr() if flow_prev is not None else None, tx.data_ptr(), ty.data_ptr(),
+        feat.data_ptr(), N, H, W, hp, wp, _stream()), tag=f"{N}x8x{H}x{W}")
+    return feat
+
+
 def warp2_lhbdc(x_before, x_after, flow_hat, flow_ab, flow_ba, return_flows=False, arith=0):
     """Fused LHBDC/model/m.py:55-63: flow glue + two warps + concat -> [N,6,H,W] (and optionally the two
     full-resolution flows [N,4,H,W])."""

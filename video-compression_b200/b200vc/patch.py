@@ -50,6 +50,8 @@ def patch(model, fuse=True):
             name, variant = _WARP_BY_CLASS[cls]
             _bind(mod, name, lambda self, img, flow, _v=variant: ops.backwarp(img, flow, _v))
         if cls == "Network" and hasattr(mod, "netBasic"):
+            if fuse:  # pyramid + per-level glue kernels (K-SPYPYR / K-SPYLEVEL), convolutions untouched
+                _bind(mod, "forward", lhbdc.Network.forward)
             # SPyNet calls the module-level ``backwarp`` of LHBDC/model/flow.py (flow.py:98): swap the global.
             host = sys.modules.get(type(mod).__module__)
             if host is not None and hasattr(host, "backwarp"):

@@ -195,24 +195,6 @@ warp2_half_sse_kernel(const float* __restrict__ x1, const float* __restrict__ x2
     partials[((int64_t)n * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = tot;
 }
 
-static WarpGeom make_geom(int H, int W, int variant, int arith) {
-  WarpGeom g;
-  g.H = H;
-  g.W = W;
-  g.variant = variant;
-  g.arith = arith;
-  if (variant == B200VC_WARP_FLEX) {
-    g.den_x = (float)W;
-    g.den_y = (float)H;
-  } else {
-    g.den_x = (float)(((double)W - 1.0) / 2.0);
-    g.den_y = (float)(((double)H - 1.0) / 2.0);
-  }
-  g.inv_x = 1.0f / g.den_x;
-  g.inv_y = 1.0f / g.den_y;
-  return g;
-}
-
 }  // namespace b200vc
 
 using namespace b200vc;

@@ -7,10 +7,27 @@ namespace b200vc {
 
 struct WarpGeom {
   int H, W;
-  float inv_x, inv_y;  // 1.0f / float((W-1)/2)  (ATen CUDA: tensor / python scalar == tensor * (1/scalar))
+  float inv_x, inv_y;  // float(1.0 / ((W-1)/2))  (ATen CUDA: tensor / python scalar == tensor * float(1/scalar))
   float den_x, den_y;  // float((W-1)/2)         (ARITH_TRUE_DIV form)
   int variant, arith;
 };
+
+// Reference arithmetic of the flow normalisation (see coords()): the divisor is the python float (W-1)/2 cast to fp32.
+inline WarpGeom make_geom(int H, int W, int variant, int arith) {
+  WarpGeom g;
+  g.H = H;
+  g.W = W;
+  g.variant = variant;
+  g.arith = arith;
+  const double dx = variant == B200VC_WARP_FLEX ? (double)W : ((double)W - 1.0) / 2.0;
+  const double dy = variant == B200VC_WARP_FLEX ? (double)H : ((double)H - 1.0) / 2.0;
+  g.den_x = (float)dx;
+  g.den_y = (float)dy;
+  // ATen CUDA div by a python scalar multiplies by float(1.0 / double(scalar)): reciprocal in double, then cast
+  g.inv_x = (float)(1.0 / dx);
+  g.inv_y = (float)(1.0 / dy);
+  return g;
+}
 
 // Normalised grid coordinate -> source pixel coordinate, exactly as ATen's grid_sampler_compute_source_index.
 __device__ __forceinline__ float unnormalize(float g, int size, bool align_corners, bool border, int arith) {
