@@ -175,7 +175,7 @@ def spynet_pyramid(frame, preprocess=True, max_poolings=5):
     lib = _lib.load()
     total = sum(h * w for h, w in sizes[1:]) + (H * W if preprocess else 0)
     _run("spynet_pyramid_f32", 4 * 3 * N * (H * W + total), lambda: lib.b200vc_spynet_pyramid_f32(
-        fp, fbs, ptrs, N, H, W, n_levels, int(bool(preprocess)), _stream()))
+        fp, fbs, ptrs, N, H, W, n_levels, int(bool(preprocess)), _stream()), tag=f"{N}x3x{H}x{W}")
     return levels[::-1]
 
 

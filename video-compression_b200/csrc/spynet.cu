@@ -20,6 +20,10 @@
 
 namespace b200vc {
 
+int launch_spynet_level_tma(const float* first, int64_t first_bs, const float* second, int64_t second_bs,
+                            const float* flow_prev, const float* tab_x, const float* tab_y, float* feat, int N, int H,
+                            int W, int hp, int wp, float sy, float sx, const WarpGeom& g, cudaStream_t st);  // warp_tma.cu
+
 // ------------------------------------------------------------------------------------------------ pyramid
 constexpr int kPyrMaxLevels = 5;
 constexpr int kPyrTileW = 64, kPyrTileH = 32;  // level-0 pixels per CTA: 2^5-aligned, so every level stays CTA-local
@@ -35,7 +39,7 @@ __device__ __forceinline__ float pool4(float a, float b, float c, float d) {
   return __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(0.f, a), b), c), d), 4.f);
 }
 
-template <bool PRE>
+template <bool PRE, bool VEC>
 __global__ void __launch_bounds__(256)
 spynet_pyramid_kernel(const float* __restrict__ in, int64_t in_bs, PyrArgs a) {
   __shared__ float s[2][kPyrTileH / 2][kPyrTileW / 2];  // ping-pong of the pooled tile
@@ -51,35 +55,66 @@ spynet_pyramid_kernel(const float* __restrict__ in, int64_t in_bs, PyrArgs a) {
   float* dst0 = a.lvl[0] + ((int64_t)n * 3 + c_out) * H * W;
   const int x0 = blockIdx.x * kPyrTileW, y0 = blockIdx.y * kPyrTileH;
 
-  // level 0 (copy / preprocess) and level 1: every thread owns two 2x2 blocks (32 x 16 blocks per tile)
+  if (VEC) {
+    // level 0 (copy / preprocess) and level 1: every thread owns 4 x 2 pixels = two 2x2 blocks (W % 4 == 0: 16-byte
+    // loads / stores, a row of the tile is 16 threads x 16 B)
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads
+    const int x = x0 + 4 * tx, y = y0 + 2 * ty;
+    float4 r[2];
 #pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    const int bx = threadIdx.x & 31, by = (threadIdx.x >> 5) + 8 * k;
-    const int x = x0 + 2 * bx, y = y0 + 2 * by;
-    float v[2][2];
-#pragma unroll
-    for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-      for (int dx = 0; dx < 2; ++dx) {
-        const bool ok = (x + dx < W) && (y + dy < H);
-        float t = ok ? __ldg(src + (int64_t)(y + dy) * W + x + dx) : 0.f;
-        if (PRE) t = __fmul_rn(__fsub_rn(t, mean), inv);
-        v[dy][dx] = t;
-        if (PRE && ok) dst0[(int64_t)(y + dy) * W + x + dx] = t;
+    for (int dy = 0; dy < 2; ++dy) {
+      const bool ok = (x < W) && (y + dy < H);
+      float4 t = ok ? ld_stream4(src + (int64_t)(y + dy) * W + x) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (PRE) {
+        t.x = __fmul_rn(__fsub_rn(t.x, mean), inv); t.y = __fmul_rn(__fsub_rn(t.y, mean), inv);
+        t.z = __fmul_rn(__fsub_rn(t.z, mean), inv); t.w = __fmul_rn(__fsub_rn(t.w, mean), inv);
+        if (ok) *reinterpret_cast<float4*>(dst0 + (int64_t)(y + dy) * W + x) = t;
       }
-    const float p = pool4(v[0][0], v[0][1], v[1][0], v[1][1]);
-    s[0][by][bx] = p;
+      r[dy] = t;
+    }
+    const float p0 = pool4(r[0].x, r[0].y, r[1].x, r[1].y), p1 = pool4(r[0].z, r[0].w, r[1].z, r[1].w);
+    s[0][ty][2 * tx] = p0;
+    s[0][ty][2 * tx + 1] = p1;
     if (a.levels >= 1) {
-      const int px = (x0 >> 1) + bx, py = (y0 >> 1) + by;
-      if (px < a.w[1] && py < a.h[1]) a.lvl[1][(((int64_t)n * 3 + c_out) * a.h[1] + py) * a.w[1] + px] = p;
+      const int px = (x0 >> 1) + 2 * tx, py = (y0 >> 1) + ty;
+      float* d1 = a.lvl[1] + (((int64_t)n * 3 + c_out) * a.h[1] + py) * a.w[1] + px;
+      if (py < a.h[1]) {
+        if (px + 1 < a.w[1]) *reinterpret_cast<float2*>(d1) = make_float2(p0, p1);  // w[1] = W/2 is even: 8-byte aligned
+        else if (px < a.w[1]) d1[0] = p0;
+      }
+    }
+  } else {
+    // level 0 (copy / preprocess) and level 1: every thread owns two 2x2 blocks (32 x 16 blocks per tile)
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int bx = threadIdx.x & 31, by = (threadIdx.x >> 5) + 8 * k;
+      const int x = x0 + 2 * bx, y = y0 + 2 * by;
+      float v[2][2];
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const bool ok = (x + dx < W) && (y + dy < H);
+          float t = ok ? __ldg(src + (int64_t)(y + dy) * W + x + dx) : 0.f;
+          if (PRE) t = __fmul_rn(__fsub_rn(t, mean), inv);
+          v[dy][dx] = t;
+          if (PRE && ok) dst0[(int64_t)(y + dy) * W + x + dx] = t;
+        }
+      const float p = pool4(v[0][0], v[0][1], v[1][0], v[1][1]);
+      s[0][by][bx] = p;
+      if (a.levels >= 1) {
+        const int px = (x0 >> 1) + bx, py = (y0 >> 1) + by;
+        if (px < a.w[1] && py < a.h[1]) a.lvl[1][(((int64_t)n * 3 + c_out) * a.h[1] + py) * a.w[1] + px] = p;
+      }
     }
   }
   // levels 2..5 from shared memory: level l reads buffer (l & 1) and writes the other one (level 1 sits in s[0])
-  int tw = kPyrTileW / 2, th = kPyrTileH / 2;
-  for (int l = 2; l <= a.levels; ++l) {
+  // (fully unrolled: a runtime index into the by-value argument struct would force a local-memory copy of it)
+#pragma unroll
+  for (int l = 2; l <= kPyrMaxLevels; ++l) {
+    if (l > a.levels) break;
     __syncthreads();
-    tw >>= 1;
-    th >>= 1;
+    const int tw = kPyrTileW >> l, th = kPyrTileH >> l;
     const int from = l & 1, to = from ^ 1;
     if (threadIdx.x < tw * th) {
       const int bx = threadIdx.x % tw, by = threadIdx.x / tw;
@@ -107,55 +142,86 @@ __device__ __forceinline__ UpAC up_ac_index(int dst, int in_size, float scale) {
   return r;
 }
 
-// One thread per output pixel of a 32 x 8 tile (the gather-kernel geometry of warp.cu).
+// One thread per PX output pixels (rows y, y+8, ...) of a 32 x 8*PX tile (the gather-kernel geometry of warp.cu;
+// the kernel is latency-bound -- flow taps, then image taps -- so PX independent chains are kept in flight).
 // feat[n] = [ first (3) | backwarp(second, up) (3) | up (2) ],  up = 2 * upsample_x2(flow_prev), replicate-padded.
+template <int PX>
 __global__ void __launch_bounds__(kWarpThreads)
 spynet_level_kernel(const float* __restrict__ first, int64_t first_bs, const float* __restrict__ second,
                     int64_t second_bs, const float* __restrict__ flow_prev, const float* __restrict__ tab_x,
                     const float* __restrict__ tab_y, float* __restrict__ feat, int hp, int wp, float scale_y,
                     float scale_x, WarpGeom g) {
+  constexpr int kRows = kWarpThreads / 32;
   const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int y = blockIdx.y * (kWarpThreads / 32) + (threadIdx.x >> 5);
+  const int y0 = blockIdx.y * (kRows * PX) + (threadIdx.x >> 5);
   const int n = blockIdx.z;
-  if (x >= g.W || y >= g.H) return;
+  if (x >= g.W) return;
   const int HW = g.H * g.W;
-  const int o = y * g.W + x;
-  float u = 0.f, v = 0.f;
+  float u[PX], v[PX];
+#pragma unroll
+  for (int k = 0; k < PX; ++k) u[k] = v[k] = 0.f;
   if (flow_prev != nullptr) {
     // replicate pad (flow.py:95-96): the last row / column of the upsampled flow is repeated once
-    const int xs = min(x, 2 * wp - 1), ys = min(y, 2 * hp - 1);
-    const UpAC ux = up_ac_index(xs, wp, scale_x), uy = up_ac_index(ys, hp, scale_y);
+    const int xs = min(x, 2 * wp - 1);
+    const UpAC ux = up_ac_index(xs, wp, scale_x);
     const float* fu = flow_prev + (int64_t)n * 2 * hp * wp;
     const float* fv = fu + hp * wp;
-    const int o00 = uy.i0 * wp + ux.i0, o01 = uy.i0 * wp + ux.i1, o10 = uy.i1 * wp + ux.i0, o11 = uy.i1 * wp + ux.i1;
-    const float ua = __ldg(fu + o00), ub = __ldg(fu + o01), uc = __ldg(fu + o10), ud = __ldg(fu + o11);
-    const float va = __ldg(fv + o00), vb = __ldg(fv + o01), vc = __ldg(fv + o10), vd = __ldg(fv + o11);
-    const float ui = __fmaf_rn(uy.l0, __fmaf_rn(ux.l0, ua, __fmul_rn(ux.l1, ub)),
-                               __fmul_rn(uy.l1, __fmaf_rn(ux.l0, uc, __fmul_rn(ux.l1, ud))));
-    const float vi = __fmaf_rn(uy.l0, __fmaf_rn(ux.l0, va, __fmul_rn(ux.l1, vb)),
-                               __fmul_rn(uy.l1, __fmaf_rn(ux.l0, vc, __fmul_rn(ux.l1, vd))));
-    u = __fmul_rn(ui, 2.0f);
-    v = __fmul_rn(vi, 2.0f);
+    float ta[PX][4], tb[PX][4];
+    UpAC uy[PX];
+#pragma unroll
+    for (int k = 0; k < PX; ++k) {
+      const int ys = min(min(y0 + k * kRows, g.H - 1), 2 * hp - 1);
+      uy[k] = up_ac_index(ys, hp, scale_y);
+      const int o00 = uy[k].i0 * wp + ux.i0, o01 = uy[k].i0 * wp + ux.i1, o10 = uy[k].i1 * wp + ux.i0,
+                o11 = uy[k].i1 * wp + ux.i1;
+      ta[k][0] = __ldg(fu + o00); ta[k][1] = __ldg(fu + o01); ta[k][2] = __ldg(fu + o10); ta[k][3] = __ldg(fu + o11);
+      tb[k][0] = __ldg(fv + o00); tb[k][1] = __ldg(fv + o01); tb[k][2] = __ldg(fv + o10); tb[k][3] = __ldg(fv + o11);
+    }
+#pragma unroll
+    for (int k = 0; k < PX; ++k) {
+      const float ui = __fmaf_rn(uy[k].l0, __fmaf_rn(ux.l0, ta[k][0], __fmul_rn(ux.l1, ta[k][1])),
+                                 __fmul_rn(uy[k].l1, __fmaf_rn(ux.l0, ta[k][2], __fmul_rn(ux.l1, ta[k][3]))));
+      const float vi = __fmaf_rn(uy[k].l0, __fmaf_rn(ux.l0, tb[k][0], __fmul_rn(ux.l1, tb[k][1])),
+                                 __fmul_rn(uy[k].l1, __fmaf_rn(ux.l0, tb[k][2], __fmul_rn(ux.l1, tb[k][3]))));
+      u[k] = __fmul_rn(ui, 2.0f);
+      v[k] = __fmul_rn(vi, 2.0f);
+    }
   }
-  float ix, iy;
-  coords<B200VC_WARP_LHBDC, true>(g, x, y, u, v, __ldg(tab_x + x), __ldg(tab_y + y), ix, iy);
-  const Taps t = make_taps<true>(ix, iy, g.H, g.W);
+  const float tx = __ldg(tab_x + x);
+  Taps t[PX];
+#pragma unroll
+  for (int k = 0; k < PX; ++k) {
+    const int y = min(y0 + k * kRows, g.H - 1);
+    float ix, iy;
+    coords<B200VC_WARP_LHBDC, true>(g, x, y, u[k], v[k], tx, __ldg(tab_y + y), ix, iy);
+    t[k] = make_taps<true>(ix, iy, g.H, g.W);
+  }
   const float* sp = second + (int64_t)n * second_bs;
   const float* fp = first + (int64_t)n * first_bs;
-  float r[3], f[3];
+  float r[PX][3], f[PX][3];
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    r[c] = sample<true>(sp + (int64_t)c * HW, t);
-    f[c] = __ldg(fp + (int64_t)c * HW + o);
-  }
-  float* op = feat + (int64_t)n * 8 * HW + o;
+  for (int k = 0; k < PX; ++k) {
+    const int y = min(y0 + k * kRows, g.H - 1);
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    op[(int64_t)c * HW] = f[c];
-    op[(int64_t)(3 + c) * HW] = r[c];
+    for (int c = 0; c < 3; ++c) {
+      r[k][c] = sample<true>(sp + (int64_t)c * HW, t[k]);
+      f[k][c] = __ldg(fp + (int64_t)c * HW + y * g.W + x);
+    }
   }
-  op[(int64_t)6 * HW] = u;
-  op[(int64_t)7 * HW] = v;
+#pragma unroll
+  for (int k = 0; k < PX; ++k) {
+    const int y = y0 + k * kRows;
+    if (y < g.H) {
+      float* op = feat + (int64_t)n * 8 * HW + y * g.W + x;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        op[(int64_t)c * HW] = f[k][c];
+        op[(int64_t)(3 + c) * HW] = r[k][c];
+      }
+      op[(int64_t)6 * HW] = u[k];
+      op[(int64_t)7 * HW] = v[k];
+    }
+  }
 }
 
 }  // namespace b200vc
@@ -190,10 +256,17 @@ extern "C" int b200vc_spynet_pyramid_f32(const float* frame, int64_t frame_bs, f
   }
   dim3 grid((W + kPyrTileW - 1) / kPyrTileW, (H + kPyrTileH - 1) / kPyrTileH, N * 3);
   cudaStream_t st = (cudaStream_t)stream;
-  if (preprocess)
-    spynet_pyramid_kernel<true><<<grid, 256, 0, st>>>(frame, frame_bs, a);
-  else
-    spynet_pyramid_kernel<false><<<grid, 256, 0, st>>>(frame, frame_bs, a);
+  // 16-byte path: rows of the frame and of level 0 must start 16-byte aligned
+  const bool vec = (W % 4 == 0) && (frame_bs % 4 == 0) && ((reinterpret_cast<uintptr_t>(frame) & 15) == 0) &&
+                   (!preprocess || (reinterpret_cast<uintptr_t>(levels[0]) & 15) == 0) &&
+                   (n_levels < 1 || (reinterpret_cast<uintptr_t>(levels[1]) & 7) == 0);
+  if (preprocess) {
+    if (vec) spynet_pyramid_kernel<true, true><<<grid, 256, 0, st>>>(frame, frame_bs, a);
+    else spynet_pyramid_kernel<true, false><<<grid, 256, 0, st>>>(frame, frame_bs, a);
+  } else {
+    if (vec) spynet_pyramid_kernel<false, true><<<grid, 256, 0, st>>>(frame, frame_bs, a);
+    else spynet_pyramid_kernel<false, false><<<grid, 256, 0, st>>>(frame, frame_bs, a);
+  }
   return check_launch("spynet_pyramid_f32");
 }
 
@@ -213,9 +286,20 @@ extern "C" int b200vc_spynet_level_f32(const float* first, int64_t first_bs, con
   // area_pixel_compute_scale(align_corners=True): (T)(in - 1) / (out - 1), 0 when out == 1
   const float sy = (flow_prev && 2 * hp > 1) ? (float)(hp - 1) / (float)(2 * hp - 1) : 0.f;
   const float sx = (flow_prev && 2 * wp > 1) ? (float)(wp - 1) / (float)(2 * wp - 1) : 0.f;
+  {
+    const int rc = launch_spynet_level_tma(first, first_bs, second, second_bs, flow_prev, tab_x, tab_y, feat, N, H, W,
+                                           hp, wp, sy, sx, g, (cudaStream_t)stream);
+    if (rc != B200VC_EUNSUPPORTED) return rc;
+  }
   const int rows = kWarpThreads / 32;
-  dim3 grid((W + 31) / 32, (H + rows - 1) / rows, N);
-  spynet_level_kernel<<<grid, kWarpThreads, 0, (cudaStream_t)stream>>>(first, first_bs, second, second_bs, flow_prev,
-                                                                      tab_x, tab_y, feat, hp, wp, sy, sx, g);
+  // 2 pixels per thread once the plane is large enough to still fill the machine (same rule as warp_f32)
+  const int px = (int64_t)N * H * W >= (1 << 19) ? 2 : 1;
+  dim3 grid((W + 31) / 32, (H + rows * px - 1) / (rows * px), N);
+  if (px == 2)
+    spynet_level_kernel<2><<<grid, kWarpThreads, 0, (cudaStream_t)stream>>>(first, first_bs, second, second_bs,
+                                                                         flow_prev, tab_x, tab_y, feat, hp, wp, sy, sx, g);
+  else
+    spynet_level_kernel<1><<<grid, kWarpThreads, 0, (cudaStream_t)stream>>>(first, first_bs, second, second_bs,
+                                                                         flow_prev, tab_x, tab_y, feat, hp, wp, sy, sx, g);
   return check_launch("spynet_level_f32");
 }

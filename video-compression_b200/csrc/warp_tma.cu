@@ -27,11 +27,30 @@ constexpr int kSmemBytes = kBoxBytes + 128;  // + alignment slack
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-template <int VARIANT>
-__global__ void __launch_bounds__(kThreads)
+// SPY = SPyNet level form (spynet.cu, LHBDC/model/flow.py:93-98): `flow` is the PREVIOUS level's flow [N,2,hp,wp]
+// (or NULL = zeros); the displacement is 2 * its x2 align_corners=True upsample, replicate-padded; `out` is the
+// 8-plane conv input [first | warped second | up] and `img` is `second`.
+struct SpyArgs {
+  const float* first;
+  int64_t first_bs;
+  int hp, wp;
+  float sy, sx;
+};
+
+__device__ __forceinline__ void up_ac(int dst, int in_size, float scale, int& i0, int& i1, float& l0, float& l1) {
+  // ATen upsample_bilinear2d, align_corners=True: src = scale * dst (see spynet.cu)
+  const float src = __fmul_rn(scale, (float)dst);
+  i0 = (int)src;
+  i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
+  l1 = __fsub_rn(src, (float)i0);
+  l0 = __fsub_rn(1.f, l1);
+}
+
+template <int VARIANT, bool SPY>
+__global__ void __launch_bounds__(kThreads, SPY ? 3 : 1)
 warp_tma_kernel(const __grid_constant__ CUtensorMap map_img, const float* __restrict__ img,
                 const float* __restrict__ flow, const float* __restrict__ tab_x, const float* __restrict__ tab_y,
-                float* __restrict__ out, int64_t out_bs, WarpGeom g) {
+                float* __restrict__ out, int64_t out_bs, WarpGeom g, SpyArgs spy) {
   constexpr bool BORDER = (VARIANT != B200VC_WARP_FLEX);
   extern __shared__ uint8_t smem_raw[];
   float* tile = reinterpret_cast<float*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));  // [3][kBH][kBW]
@@ -53,13 +72,59 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap map_img, const float* __rest
   }
 
   // ---- phase A: flow -> source coordinates (all 16 loads of the thread in flight together)
-  const float* fbase = flow + (int64_t)n * 2 * HW;
   float u[kPX], v[kPX];
+  if (!SPY) {
+    const float* fbase = flow + (int64_t)n * 2 * HW;
 #pragma unroll
-  for (int k = 0; k < kPX; ++k) {
-    const int y = min(blockIdx.y * kTH + ty + 4 * k, g.H - 1);
-    u[k] = __ldg(fbase + y * g.W + xc);
-    v[k] = __ldg(fbase + HW + y * g.W + xc);
+    for (int k = 0; k < kPX; ++k) {
+      const int y = min(blockIdx.y * kTH + ty + 4 * k, g.H - 1);
+      u[k] = __ldg(fbase + y * g.W + xc);
+      v[k] = __ldg(fbase + HW + y * g.W + xc);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < kPX; ++k) u[k] = v[k] = 0.f;
+    if (flow != nullptr) {
+      const int hp = spy.hp, wp = spy.wp;
+      const float* fu = flow + (int64_t)n * 2 * hp * wp;
+      const float* fv = fu + hp * wp;
+      int xi0, xi1;
+      float xl0, xl1;
+      up_ac(min(xc, 2 * wp - 1), wp, spy.sx, xi0, xi1, xl0, xl1);  // replicate pad = clamp of the destination index
+      // two batches of 4 pixels: 32 taps in flight per thread without the register cost of all 64
+#pragma unroll
+      for (int k0 = 0; k0 < kPX; k0 += 4) {
+        float ta[4][4], tb[4][4], yl0[4], yl1[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int y = min(min(blockIdx.y * kTH + ty + 4 * (k0 + j), g.H - 1), 2 * hp - 1);
+          int yi0, yi1;
+          up_ac(y, hp, spy.sy, yi0, yi1, yl0[j], yl1[j]);
+          const int o00 = yi0 * wp + xi0, o01 = yi0 * wp + xi1, o10 = yi1 * wp + xi0, o11 = yi1 * wp + xi1;
+          ta[j][0] = __ldg(fu + o00); ta[j][1] = __ldg(fu + o01); ta[j][2] = __ldg(fu + o10); ta[j][3] = __ldg(fu + o11);
+          tb[j][0] = __ldg(fv + o00); tb[j][1] = __ldg(fv + o01); tb[j][2] = __ldg(fv + o10); tb[j][3] = __ldg(fv + o11);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float ui = __fmaf_rn(yl0[j], __fmaf_rn(xl0, ta[j][0], __fmul_rn(xl1, ta[j][1])),
+                                     __fmul_rn(yl1[j], __fmaf_rn(xl0, ta[j][2], __fmul_rn(xl1, ta[j][3]))));
+          const float vi = __fmaf_rn(yl0[j], __fmaf_rn(xl0, tb[j][0], __fmul_rn(xl1, tb[j][1])),
+                                     __fmul_rn(yl1[j], __fmaf_rn(xl0, tb[j][2], __fmul_rn(xl1, tb[j][3]))));
+          u[k0 + j] = __fmul_rn(ui, 2.0f);
+          v[k0 + j] = __fmul_rn(vi, 2.0f);
+        }
+      }
+    }
+    // planes 6, 7 of the level's conv input = the upsampled flow itself
+    float* up = out + (int64_t)n * out_bs + (int64_t)6 * HW;
+#pragma unroll
+    for (int k = 0; k < kPX; ++k) {
+      const int y = blockIdx.y * kTH + ty + 4 * k;
+      if (xin && y < g.H) {
+        up[y * g.W + x] = u[k];
+        up[HW + y * g.W + x] = v[k];
+      }
+    }
   }
   const float txv = BORDER ? __ldg(tab_x + xc) : 0.f;
   float ix[kPX], iy[kPX];
@@ -104,7 +169,27 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap map_img, const float* __rest
   __syncthreads();
   const int bx0 = s_box[0], by0 = s_box[1];
   const bool staged = s_box[2] != 0;
-  float* op = out + (int64_t)n * out_bs;
+  float* op = out + (int64_t)n * out_bs + (SPY ? (int64_t)3 * HW : 0);
+  if (SPY) {
+    // planes 0-2 = `first`, copied while the box is in flight
+    const float* fp = spy.first + (int64_t)n * spy.first_bs;
+    float* o0 = out + (int64_t)n * out_bs;
+    float f[kPX][3];
+#pragma unroll
+    for (int k = 0; k < kPX; ++k) {
+      const int y = min(blockIdx.y * kTH + ty + 4 * k, g.H - 1);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) f[k][c] = __ldg(fp + (int64_t)c * HW + y * g.W + xc);
+    }
+#pragma unroll
+    for (int k = 0; k < kPX; ++k) {
+      const int y = blockIdx.y * kTH + ty + 4 * k;
+      if (xin && y < g.H) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) o0[(int64_t)c * HW + y * g.W + x] = f[k][c];
+      }
+    }
+  }
 
   if (staged) {
     // wait for the box (phase 0 of a one-shot barrier)
@@ -377,20 +462,57 @@ int launch_warp_tma(const float* img, int64_t img_bs, const float* flow, const f
 #define B200VC_WT_LAUNCH(V)                                                                                     \
   do {                                                                                                          \
     if (dev >= 0 && dev < 64 && !configured[dev][V]) {                                                          \
-      if (cudaFuncSetAttribute(warp_tma_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) !=  \
+      if (cudaFuncSetAttribute(warp_tma_kernel<V, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) !=  \
           cudaSuccess) {                                                                                        \
         (void)cudaGetLastError();                                                                               \
         return B200VC_EUNSUPPORTED;                                                                             \
       }                                                                                                         \
       configured[dev][V] = true;                                                                                \
     }                                                                                                           \
-    warp_tma_kernel<V><<<grid, kThreads, kSmemBytes, st>>>(map, img, flow, tab_x, tab_y, out, out_bs, gd);        \
+    warp_tma_kernel<V, false><<<grid, kThreads, kSmemBytes, st>>>(map, img, flow, tab_x, tab_y, out, out_bs, gd, SpyArgs{});  \
   } while (0)
   if (g.variant == B200VC_WARP_LHBDC) B200VC_WT_LAUNCH(0);
   else if (g.variant == B200VC_WARP_FLEX) B200VC_WT_LAUNCH(1);
   else B200VC_WT_LAUNCH(2);
 #undef B200VC_WT_LAUNCH
   return check_launch("warp_f32(tma)");
+}
+
+// SPyNet level through the staged kernel; B200VC_EUNSUPPORTED when the level does not qualify (spynet.cu then uses
+// its gather kernel).  Upsampled flows are smooth by construction, so the footprint test practically always passes.
+int launch_spynet_level_tma(const float* first, int64_t first_bs, const float* second, int64_t second_bs,
+                            const float* flow_prev, const float* tab_x, const float* tab_y, float* feat, int N, int H,
+                            int W, int hp, int wp, float sy, float sx, const WarpGeom& g, cudaStream_t st) {
+  using namespace wt;
+  static const int enabled = []() {
+    const char* e = getenv("B200VC_SPYNET_TMA");
+    return e ? atoi(e) : 1;
+  }();
+  // measured on B200 (tools/spynet_time.py): staged wins from ~2 Mpx per launch (N=4 1088x1920: 105 vs 121 us);
+  // below that the launch is too short for the box round trip to pay and the gather kernel is equal or better
+  if (!enabled || second_bs != (int64_t)3 * H * W || W % 4 != 0 || (int64_t)N * H * W < (1 << 21) ||
+      (int64_t)H * W < 128 * 128 || (reinterpret_cast<uintptr_t>(second) & 15u) != 0 || (int64_t)N * 3 >= (1 << 30))
+    return B200VC_EUNSUPPORTED;
+  CUtensorMap map;
+  if (!make_img_map(&map, second, N, H, W)) return B200VC_EUNSUPPORTED;
+  static bool configured[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !configured[dev]) {
+    if (cudaFuncSetAttribute(warp_tma_kernel<B200VC_WARP_LHBDC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             kSmemBytes) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return B200VC_EUNSUPPORTED;
+    }
+    configured[dev] = true;
+  }
+  dim3 grid((W + kTW - 1) / kTW, (H + kTH - 1) / kTH, N);
+  WarpGeom gd = g;
+  gd.arith = 0;
+  SpyArgs spy{first, first_bs, hp, wp, sy, sx};
+  warp_tma_kernel<B200VC_WARP_LHBDC, true><<<grid, kThreads, kSmemBytes, st>>>(map, second, flow_prev, tab_x, tab_y,
+                                                                             feat, (int64_t)8 * H * W, gd, spy);
+  return check_launch("spynet_level_f32(tma)");
 }
 
 int launch_warp2_tma(const float* xb, const float* xa, const float* flow_hat, const float* flow_ab,
