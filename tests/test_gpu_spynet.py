@@ -54,7 +54,9 @@ def test_pyramid_accepts_a_channel_slice_and_batch_stride():
         assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("shape", [(1, 34, 60), (2, 68, 120), (1, 17, 31), (1, 35, 64), (2, 136, 240), (1, 544, 960)])
+# >= 2 Mpx per launch with W % 4 == 0 takes the TMA-staged kernel (warp_tma.cu), everything else the gather kernel
+@pytest.mark.parametrize("shape", [(1, 34, 60), (2, 68, 120), (1, 17, 31), (1, 35, 64), (2, 136, 240), (1, 544, 960),
+                                   (1, 1088, 1920), (4, 544, 960), (3, 1087, 1924)])
 @pytest.mark.parametrize("amp", [0.7, 6.0])
 def test_level_is_bit_exact(shape, amp):
     from b200vc import ops
@@ -111,3 +113,25 @@ def test_flownet_matches_oracle_network(shape, strict_fp32):
     scale = want.abs().max().item()
     print(f"FlowNet {shape}: max|diff|={err:.3e} (flow magnitude {scale:.3e}) bit-exact={(got == want).float().mean().item():.5f}")
     assert err <= 1e-5 * max(1.0, scale)
+
+
+def test_level_gather_kernel_at_full_hd():
+    """The gather kernel on the shape the staged kernel normally takes (B200VC_SPYNET_TMA=0, own process)."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, torch\n"
+        "sys.path[:0] = [%r, %r, %r]\n"
+        "import test_gpu_spynet as t\n"
+        "from b200vc import ops\n"
+        "g = torch.Generator().manual_seed(5)\n"
+        "a = torch.randn(2, 3, 1088, 1920, generator=g).cuda(); b = torch.randn(2, 3, 1088, 1920, generator=g).cuda()\n"
+        "f = (3 * torch.randn(2, 2, 544, 960, generator=g)).cuda()\n"
+        "assert torch.equal(ops.spynet_level(a, b, f), t._torch_level(a, b, f))\n"
+        "print('ok')\n"
+    ) % (os.path.dirname(__file__), os.path.dirname(os.path.dirname(__file__)),
+         os.path.join(os.path.dirname(os.path.dirname(__file__)), "video-compression_b200"))
+    env = dict(os.environ, B200VC_SPYNET_TMA="0")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
