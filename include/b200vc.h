@@ -107,6 +107,15 @@ B200VC_API int b200vc_warp2_half_sse_f32(const float* x1, const float* x2, const
                                          const float* x_cur, const float* tab_x, const float* tab_y, float* pred,
                                          double* partials, int N, int H, int W, int variant, void* stream);
 
+/* Single-reference search form (OJSP2025/video_model.py:621-666: x_hat = self.warp(ref_frame, est_mv);
+ * PSNR(x, x_hat) per candidate down-sampling ratio): warp + squared error against x_cur, no clamp.
+ *   img, x_cur [N,3,H,W]; flow [N,2,H,W]; pred (nullable) [N,3,H,W] receives the warped frame;
+ *   partials double[N * b200vc_warp2_half_sse_blocks(H, W)] as above.
+ */
+B200VC_API int b200vc_warp_sse_f32(const float* img, const float* flow, const float* x_cur, const float* tab_x,
+                                   const float* tab_y, float* pred, double* partials, int N, int H, int W,
+                                   int variant, void* stream);
+
 /* ------------------------------------------------------------------------------ SPyNet glue
  * Replaces the non-convolutional part of Network.forward (LHBDC/model/flow.py:78-101).
  *

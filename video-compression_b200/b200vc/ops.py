@@ -255,6 +255,28 @@ def warp2_half_sse(x1, x2, flow1, flow2, x_cur, variant="ac1", want_pred=False):
     return sum_partials(part, nb, N), pred
 
 
+def warp_sse(img, flow, x_cur, variant="ac1", want_pred=False):
+    """Single-reference search form (OJSP2025/video_model.py:643-645): ``x_hat = warp(img, flow)`` and the squared
+    error against ``x_cur`` in one kernel.  Returns (sse[N] float64, x_hat or None); MSE = sse / (3*H*W)."""
+    if variant not in _VARIANTS:
+        raise ValueError(f"warp_sse: unknown variant {variant!r}")
+    img, xc = _contig(img, "warp_sse(img)"), _contig(x_cur, "warp_sse(x_cur)")
+    flow = _contig(flow, "warp_sse(flow)")
+    N, C, H, W = img.shape
+    if C != 3 or xc.shape != img.shape or tuple(flow.shape) != (N, 2, H, W):
+        raise RuntimeError("warp_sse: expected [N,3,H,W] images and an [N,2,H,W] flow")
+    tx, ty = (None, None) if variant == "flex" else grid_tables(variant, H, W, img.device)
+    lib = _lib.load()
+    nb = lib.b200vc_warp2_half_sse_blocks(H, W)
+    part = torch.empty(N * nb, device=img.device, dtype=torch.float64)
+    pred = torch.empty_like(img) if want_pred else None
+    p = lambda t: t.data_ptr() if t is not None else None
+    _run("warp_sse_f32", (8 + 3 * int(want_pred)) * 4 * N * H * W, lambda: lib.b200vc_warp_sse_f32(
+        img.data_ptr(), flow.data_ptr(), xc.data_ptr(), p(tx), p(ty), p(pred), part.data_ptr(), N, H, W,
+        _VARIANTS[variant], _stream()), tag=f"{N}x3x{H}x{W}")
+    return sum_partials(part, nb, N), pred
+
+
 # ------------------------------------------------------------------------------- blend / residual
 def reduce_blocks(elems_per_sample):
     return _lib.load().b200vc_reduce_blocks(int(elems_per_sample))

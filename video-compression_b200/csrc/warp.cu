@@ -195,6 +195,46 @@ warp2_half_sse_kernel(const float* __restrict__ x1, const float* __restrict__ x2
     partials[((int64_t)n * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = tot;
 }
 
+// Single-reference search form (OJSP2025/video_model.py:621-666: x_hat = warp(ref_frame, est_mv) ; PSNR(x, x_hat)
+// = 10 log10(1 / mean((x - x_hat)^2)) for each of 32 candidate ratios at 2160 x 3840): warp + squared error in one
+// pass; the warped frame is written only when asked for (32 B/px algorithmic instead of 56 + the torch MSE chain).
+template <int VARIANT>
+__global__ void __launch_bounds__(kWarpThreads)
+warp_sse_kernel(const float* __restrict__ img, const float* __restrict__ flow, const float* __restrict__ x_cur,
+                const float* __restrict__ tab_x, const float* __restrict__ tab_y, float* __restrict__ pred_out,
+                double* __restrict__ partials, WarpGeom g) {
+  constexpr bool BORDER = (VARIANT != B200VC_WARP_FLEX);
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * (kWarpThreads / 32) + (threadIdx.x >> 5);
+  const int n = blockIdx.z;
+  const int HW = g.H * g.W;
+  float sse = 0.f;
+  if (x < g.W && y < g.H) {
+    const int o = y * g.W + x;
+    const float tx = BORDER ? __ldg(tab_x + x) : 0.f, ty = BORDER ? __ldg(tab_y + y) : 0.f;
+    const float* f = flow + (int64_t)n * 2 * HW + o;
+    float ix, iy;
+    coords<VARIANT, true>(g, x, y, __ldg(f), __ldg(f + HW), tx, ty, ix, iy);
+    const Taps t = make_taps<BORDER>(ix, iy, g.H, g.W);
+    const float* ip = img + (int64_t)n * 3 * HW;
+    float r[3], c0[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      r[c] = sample<BORDER>(ip + (int64_t)c * HW, t);
+      c0[c] = __ldg(x_cur + ((int64_t)n * 3 + c) * HW + o);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      if (pred_out != nullptr) pred_out[((int64_t)n * 3 + c) * HW + o] = r[c];
+      const float d = __fsub_rn(c0[c], r[c]);
+      sse = __fmaf_rn(d, d, sse);
+    }
+  }
+  const double tot = block_sum_to_f64<kWarpThreads>(sse);
+  if (threadIdx.x == 0)
+    partials[((int64_t)n * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = tot;
+}
+
 }  // namespace b200vc
 
 using namespace b200vc;
@@ -310,4 +350,25 @@ extern "C" int b200vc_warp2_half_sse_f32(const float* x1, const float* x2, const
   else
     warp2_half_sse_kernel<2><<<grid, kWarpThreads, 0, st>>>(x1, x2, flow1, flow2, x_cur, tab_x, tab_y, pred, partials, g);
   return check_launch("warp2_half_sse_f32");
+}
+
+extern "C" int b200vc_warp_sse_f32(const float* img, const float* flow, const float* x_cur, const float* tab_x,
+                                   const float* tab_y, float* pred, double* partials, int N, int H, int W,
+                                   int variant, void* stream) {
+  B200VC_REQUIRE(img && flow && x_cur && partials, "warp_sse_f32: null pointer");
+  B200VC_REQUIRE(N > 0 && N <= 65535 && H > 0 && W > 0, "warp_sse_f32: bad shape");
+  B200VC_REQUIRE(variant >= 0 && variant <= 2, "warp_sse_f32: unknown variant %d", variant);
+  B200VC_REQUIRE(variant == B200VC_WARP_FLEX || (tab_x && tab_y), "warp_sse_f32: grid tables required");
+  B200VC_REQUIRE((int64_t)H * W < (1ll << 31), "warp_sse_f32: plane too large");
+  const WarpGeom g = make_geom(H, W, variant, 0);
+  const int rows = kWarpThreads / 32;
+  dim3 grid((W + 31) / 32, (H + rows - 1) / rows, N);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (variant == B200VC_WARP_LHBDC)
+    warp_sse_kernel<0><<<grid, kWarpThreads, 0, st>>>(img, flow, x_cur, tab_x, tab_y, pred, partials, g);
+  else if (variant == B200VC_WARP_FLEX)
+    warp_sse_kernel<1><<<grid, kWarpThreads, 0, st>>>(img, flow, x_cur, tab_x, tab_y, pred, partials, g);
+  else
+    warp_sse_kernel<2><<<grid, kWarpThreads, 0, st>>>(img, flow, x_cur, tab_x, tab_y, pred, partials, g);
+  return check_launch("warp_sse_f32");
 }
