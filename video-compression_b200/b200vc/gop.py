@@ -46,6 +46,15 @@ FLEX_GOP16 = Schedule(
 )
 
 
+# Flex-Rate.../test/testing.py:86-89: (I-frame quality, {hierarchy level: (gain row n, interpolation l)})
+FLEX_QUALITIES = (
+    (5, {0: (1, 1.), 1: (0, 0.33), 2: (0, 0.66), 3: (0, 1.)}), (6, {0: (1, 0.66), 1: (1, 1.), 2: (0, 0.33), 3: (0, 0.66)}),
+    (6, {0: (1, 0.33), 1: (1, 0.66), 2: (1, 1.), 3: (0, 0.33)}), (6, {0: (2, 1.), 1: (1, 0.33), 2: (1, 0.66), 3: (1, 1.)}),
+    (7, {0: (2, 0.66), 1: (2, 1.), 2: (1, 0.33), 3: (1, 0.66)}), (7, {0: (2, 0.33), 1: (2, 0.66), 2: (2, 1.), 3: (1, 0.33)}),
+    (7, {0: (3, 1.), 1: (2, 0.33), 2: (2, 0.66), 3: (2, 1.)}), (8, {0: (3, 1.), 1: (3, 1.), 2: (2, 0.33), 3: (2, 0.66)}),
+)
+
+
 def num_gops(num_frames, gop):
     """GOP k covers frames [k*gop, (k+1)*gop] (anchors shared); incomplete tails are dropped
     (``drop_last=True``, LHBDC/test/testing.py:117-120)."""
@@ -68,7 +77,10 @@ def psnr_from_sse(sse, n_values, data_range=255.0):
 
 class GopCoder:
     """Codes GOPs of already-resident frames with a B-frame ``model`` exposing
-    ``forward_device(x_before, x_current, x_after) -> (x_hat, bits[N], parts)``.
+    ``forward_device(x_before, x_current, x_after) -> (x_hat, bits[N], ...)`` (LHBDC ``Model``) or, with
+    ``level_quality = {hierarchy level: (n, l)}`` (one entry of ``FLEX_QUALITIES``; Flex-Rate.../test/testing.py:
+    193-200 passes ``n=[n], l=l`` per frame level), ``forward_device(x_before, x_current, x_after, [n], l)``
+    (``BidirFlowRef``).
 
     ``code(frames, crop)``: frames [G, gop+1, 3, H, W] (G independent GOPs, padded size), anchors are used
     as-is (uncoded) -- I-frame coding is outside the B-frame hot path.  Returns device tensors
@@ -76,9 +88,10 @@ class GopCoder:
     any host synchronisation.
     """
 
-    def __init__(self, model, schedule=LHBDC_GOP8):
+    def __init__(self, model, schedule=LHBDC_GOP8, level_quality=None):
         self.model = model
         self.schedule = schedule
+        self.level_quality = level_quality
 
     @torch.no_grad()
     def code(self, frames, crop, want_decoded=False):
@@ -91,11 +104,15 @@ class GopCoder:
         decoded = {0: frames[:, 0], sch.gop: frames[:, sch.gop]}
         bits = torch.zeros((G, T), device=dev, dtype=torch.float64)
         sse = torch.zeros((G, T), device=dev, dtype=torch.float64)
-        for level_frames in sch.by_level():
+        for level, level_frames in enumerate(sch.by_level()):
             xb = torch.cat([decoded[sch.refs[f][0]] for f in level_frames], 0)
             xa = torch.cat([decoded[sch.refs[f][1]] for f in level_frames], 0)
             xc = torch.cat([frames[:, f] for f in level_frames], 0)
-            x_hat, b, _ = self.model.forward_device(xb, xc, xa)
+            if self.level_quality is None:
+                x_hat, b = self.model.forward_device(xb, xc, xa)[:2]
+            else:
+                n, l = self.level_quality[level]
+                x_hat, b = self.model.forward_device(xb, xc, xa, [n], l)[:2]
             for k, f in enumerate(level_frames):
                 sl = slice(k * G, (k + 1) * G)
                 decoded[f] = x_hat[sl]
