@@ -135,6 +135,19 @@ B200VC_API int b200vc_spynet_level_f32(const float* first, int64_t first_bs, con
                                        const float* flow_prev, const float* tab_x, const float* tab_y, float* feat,
                                        int N, int H, int W, int hp, int wp, void* stream);
 
+/* ---------------------------------------------------------------- deformable convolution
+ * Replaces torchvision.ops.deform_conv2d (modulated, v2) behind DeformConv2d at ICIP2023/src/model/m.py:29-34 and
+ * ICIP2024/src/model/helpers.py:40,57.  Same tensor layouts as torchvision:
+ *   input  [N,Cin,H,W]; weight [Cout,Cin/groups,kh,kw]; bias [Cout] or NULL;
+ *   offset [N, offset_groups*kh*kw*2, Ho, Wo]  (per offset group and kernel point: dy, dx);
+ *   mask   [N, offset_groups*kh*kw, Ho, Wo] or NULL (v1);
+ *   out    [N,Cout,Ho,Wo], Ho = (H + 2*pad_h - (dil_h*(kh-1)+1)) / stride_h + 1.
+ * No im2col matrix is materialised. */
+B200VC_API int b200vc_deform_conv2d_f32(const float* input, const float* offset, const float* mask,
+                                        const float* weight, const float* bias, float* out, int N, int Cin, int H,
+                                        int W, int Cout, int kh, int kw, int stride_h, int stride_w, int pad_h,
+                                        int pad_w, int dil_h, int dil_w, int groups, int offset_groups, void* stream);
+
 /* ------------------------------------------------------------------------------------ blend / residual
  * Replaces LHBDC/model/m.py:63-67, Flex-Rate.../b_model/b_model.py:68-73, ICIP2024/src/opt_helpers.py:35-45.
  *   a, b: the two warped references [N,3,H,W] (batch strides a_bs, b_bs: may be halves of the concat

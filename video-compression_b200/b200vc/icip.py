@@ -6,8 +6,14 @@ scope, supplied by ``model.estimate_flow``), x2-upsamples and scales it, warps b
 border), blends 0.5/0.5, clamps and takes the MSE -- four full-frame tensors per candidate.  Here the warp -> blend ->
 clamp -> squared-error chain is ONE kernel per candidate (``ops.warp2_half_sse``), nothing but fp64 partials is
 written, and the host synchronises once for the whole search instead of once per candidate.
+
+Also here: the deformable alignment operator of the ICIP codecs (``torchvision.ops.DeformConv2d`` at
+``ICIP2023/src/model/m.py:29-34`` and ``ICIP2024/src/model/helpers.py:35-69`` ``OffsetDiversity``) on the K-DCN kernel.
 """
+import math
+
 import torch
+import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
@@ -56,3 +62,59 @@ def get_best_down_ratio_prediction(model, xref1, xref2, scale1, scale2, xcur, le
         if p > best_psnr:
             best, best_psnr = r, p
     return best, best_psnr.float()
+
+
+# ---------------------------------------------------------------------------------- deformable alignment
+def deform_conv_forward(mod, input, offset, mask=None):
+    """``DeformConv2d.forward`` re-bound by ``patch()`` on torchvision's own module (weights stay where they are)."""
+    return ops.deform_conv2d(input, offset, mod.weight, mod.bias, stride=mod.stride, padding=mod.padding,
+                             dilation=mod.dilation, mask=mask)
+
+
+class DeformConv2d(nn.Module):
+    """``torchvision.ops.DeformConv2d`` (constructor, parameter names / shapes / init and ``forward(input, offset,
+    mask=None)``) on the K-DCN kernel; state dicts are interchangeable with torchvision's module."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True):
+        super().__init__()
+        if in_channels % groups != 0 or out_channels % groups != 0:
+            raise ValueError("in_channels and out_channels must be divisible by groups")
+        pair = lambda v: (v, v) if isinstance(v, int) else tuple(v)
+        self.in_channels, self.out_channels, self.groups = in_channels, out_channels, groups
+        self.kernel_size, self.stride, self.padding, self.dilation = pair(kernel_size), pair(stride), pair(padding), \
+            pair(dilation)
+        self.weight = nn.Parameter(torch.empty(out_channels, in_channels // groups, *self.kernel_size))
+        self.bias = nn.Parameter(torch.empty(out_channels)) if bias else None
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        if self.bias is not None:
+            fan_in = self.weight.shape[1] * self.kernel_size[0] * self.kernel_size[1]
+            bound = 1 / math.sqrt(fan_in)
+            nn.init.uniform_(self.bias, -bound, bound)
+
+    def forward(self, input, offset, mask=None):
+        return deform_conv_forward(self, input, offset, mask)
+
+
+class OffsetDiversity(nn.Module):
+    """ICIP2024/src/model/helpers.py:35-69: flow-guided modulated deformable fusion of two reference features."""
+
+    def __init__(self, in_channel, magnitude):
+        super().__init__()
+        self.in_channel, self.magnitude = in_channel, magnitude
+        self.fusion = DeformConv2d(in_channel * 2, in_channel, kernel_size=3, padding=1, groups=2 * 8)
+
+    def prep(self, out, flow):
+        o1, o2, mask = torch.chunk(out, 3, dim=1)
+        mask = torch.sigmoid(mask)
+        offset = torch.tanh(torch.cat((o1, o2), dim=1)) * self.magnitude
+        offset = offset + flow.flip(1).repeat(1, offset.size(1) // 2, 1, 1)
+        return offset, mask
+
+    def forward(self, x1, offset1, flow1, x2, offset2, flow2):
+        offset1, mask1 = self.prep(offset1, flow1)
+        offset2, mask2 = self.prep(offset2, flow2)
+        return self.fusion(torch.cat((x1, x2), dim=1), torch.cat((offset1, offset2), dim=1),
+                           torch.cat((mask1, mask2), dim=1))
+
+    def warp(self, img, flow):
+        return ops.backwarp(img, flow, "ac1")

@@ -277,6 +277,51 @@ def warp_sse(img, flow, x_cur, variant="ac1", want_pred=False):
     return sum_partials(part, nb, N), pred
 
 
+# ------------------------------------------------------------------------- deformable convolution
+def deform_conv2d(input, offset, weight, bias=None, stride=(1, 1), padding=(0, 0), dilation=(1, 1), mask=None):
+    """``torchvision.ops.deform_conv2d`` (same signature and layouts; ICIP2023/src/model/m.py:29-34,
+    ICIP2024/src/model/helpers.py:40,57) without the im2col matrix."""
+    pair = lambda v: (int(v), int(v)) if isinstance(v, int) else (int(v[0]), int(v[1]))
+    (sh, sw), (ph, pw), (dh, dw) = pair(stride), pair(padding), pair(dilation)
+    x, off, w = _contig(input, "deform_conv2d(input)"), _contig(offset, "deform_conv2d(offset)"), \
+        _contig(weight, "deform_conv2d(weight)")
+    if x.dim() != 4 or off.dim() != 4 or w.dim() != 4:
+        raise RuntimeError("deform_conv2d: input, offset and weight must be 4-D")
+    N, Cin, H, W = x.shape
+    Cout, cin_g, kh, kw = w.shape
+    if cin_g == 0 or Cin % cin_g != 0:
+        raise RuntimeError(f"deform_conv2d: weight expects {cin_g} channels per group, input has {Cin}")
+    groups = Cin // cin_g
+    Ho = (H + 2 * ph - (dh * (kh - 1) + 1)) // sh + 1
+    Wo = (W + 2 * pw - (dw * (kw - 1) + 1)) // sw + 1
+    K = kh * kw
+    if off.shape[0] != N or off.shape[1] % (2 * K) != 0 or tuple(off.shape[2:]) != (Ho, Wo):
+        raise RuntimeError(f"deform_conv2d: offset shape {tuple(off.shape)} does not match [N, 2*og*{K}, {Ho}, {Wo}]")
+    og = off.shape[1] // (2 * K)
+    if og == 0 or Cin % og != 0:
+        raise RuntimeError(f"deform_conv2d: {og} offset groups do not divide {Cin} input channels")
+    m = None
+    if mask is not None:
+        m = _contig(mask, "deform_conv2d(mask)")
+        if tuple(m.shape) != (N, og * K, Ho, Wo):
+            raise RuntimeError(f"deform_conv2d: mask shape {tuple(m.shape)} does not match [N, {og * K}, {Ho}, {Wo}]")
+    b = None
+    if bias is not None:
+        b = _contig(bias, "deform_conv2d(bias)")
+        if tuple(b.shape) != (Cout,):
+            raise RuntimeError("deform_conv2d: bias must be [Cout]")
+    out = torch.empty((N, Cout, Ho, Wo), device=x.device, dtype=x.dtype)
+    if out.numel() == 0:
+        return out
+    lib = _lib.load()
+    p = lambda t: t.data_ptr() if t is not None else None
+    nbytes = 4 * (x.numel() + off.numel() + (m.numel() if m is not None else 0) + out.numel())
+    _run("deform_conv2d_f32", nbytes, lambda: lib.b200vc_deform_conv2d_f32(
+        x.data_ptr(), off.data_ptr(), p(m), w.data_ptr(), p(b), out.data_ptr(), N, Cin, H, W, Cout, kh, kw, sh, sw,
+        ph, pw, dh, dw, groups, og, _stream()), tag=f"{N}x{Cin}->{Cout}x{H}x{W}g{groups}")
+    return out
+
+
 # ------------------------------------------------------------------------------- blend / residual
 def reduce_blocks(elems_per_sample):
     return _lib.load().b200vc_reduce_blocks(int(elems_per_sample))

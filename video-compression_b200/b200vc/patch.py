@@ -6,7 +6,7 @@ or from CompressAI is imported here.
 import sys
 import types
 
-from . import lhbdc, modules, ops
+from . import icip, lhbdc, modules, ops
 
 _WARP_BY_CLASS = {
     "Model": ("backwarp", "lhbdc"),            # LHBDC/model/m.py:111
@@ -43,6 +43,8 @@ def patch(model, fuse=True):
             _bind(mod, "quantize", modules.gc_quantize)
             _bind(mod, "compress", modules.gc_compress)
             _bind(mod, "decompress", modules.gc_decompress)
+        elif cls == "DeformConv2d" and hasattr(mod, "weight"):     # torchvision.ops.DeformConv2d
+            _bind(mod, "forward", icip.deform_conv_forward)
         if hasattr(mod, "entropy_bottleneck") and hasattr(mod, "gaussian_conditional") and hasattr(mod, "g_a"):
             _bind(mod, "forward_bits", modules.hyperprior_forward_bits)
             _bind(mod, "symbols", modules.hyperprior_symbols)
