@@ -141,11 +141,14 @@ B200VC_API int b200vc_spynet_level_f32(const float* first, int64_t first_bs, con
  *   input  [N,Cin,H,W]; weight [Cout,Cin/groups,kh,kw]; bias [Cout] or NULL;
  *   offset [N, offset_groups*kh*kw*2, Ho, Wo]  (per offset group and kernel point: dy, dx);
  *   mask   [N, offset_groups*kh*kw, Ho, Wo] or NULL (v1);
- *   out    [N,Cout,Ho,Wo], Ho = (H + 2*pad_h - (dil_h*(kh-1)+1)) / stride_h + 1.
+ *   out    [N,Cout,Ho,Wo], Ho = (H + 2*pad_h - (dil_h*(kh-1)+1)) / stride_h + 1;
+ *   workspace (nullable) float[N*Cin*H*W], 16-byte aligned: scratch for the group-channels-last copy of the input
+ *   that the fast path samples from (used when Cin/groups is 4, 8, 12 or 16 and Cout/groups is 4, 6, 8, 12 or 16;
+ *   without it, or for other shapes, the NCHW gather kernel runs).
  * No im2col matrix is materialised. */
 B200VC_API int b200vc_deform_conv2d_f32(const float* input, const float* offset, const float* mask,
-                                        const float* weight, const float* bias, float* out, int N, int Cin, int H,
-                                        int W, int Cout, int kh, int kw, int stride_h, int stride_w, int pad_h,
+                                        const float* weight, const float* bias, float* out, float* workspace, int N,
+                                        int Cin, int H, int W, int Cout, int kh, int kw, int stride_h, int stride_w, int pad_h,
                                         int pad_w, int dil_h, int dil_w, int groups, int offset_groups, void* stream);
 
 /* ------------------------------------------------------------------------------------ blend / residual

@@ -40,12 +40,13 @@ def test_matches_torchvision_cuda(case):
     from b200vc import ops
     x, off, w, b, m, kw = _case(sum(case), *case)
     want = tv.deform_conv2d(x, off, w, b, mask=m, **kw)
-    got = ops.deform_conv2d(x, off, w, b, mask=m, **kw)
-    assert got.shape == want.shape and got.dtype == torch.float32
     scale = max(1.0, want.abs().max().item())
-    err = (got - want).abs().max().item()
-    print(f"dcn {case}: max|diff|={err:.3e} (|out| max {scale:.2f})")
-    assert err < 2e-5 * scale, err
+    for fast in (True, False):   # group-channels-last path (where the shape qualifies) and the NCHW gather kernel
+        got = ops.deform_conv2d(x, off, w, b, mask=m, use_workspace=fast, **kw)
+        assert got.shape == want.shape and got.dtype == torch.float32
+        err = (got - want).abs().max().item()
+        print(f"dcn {case} workspace={fast}: max|diff|={err:.3e} (|out| max {scale:.2f})")
+        assert err < 2e-5 * scale, err
 
 
 @pytest.mark.parametrize("use_mask,use_bias", [(False, True), (True, False), (False, False)])

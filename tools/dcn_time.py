@@ -29,9 +29,16 @@ for name, (Cin, Cout, H, W, groups) in {
     x = torch.randn(1, Cin, H, W, generator=g).cuda()
     w = (torch.randn(Cout, Cin // groups, 3, 3, generator=g) * 0.1).cuda()
     b = torch.randn(Cout, generator=g).cuda()
-    off = (2.0 * torch.randn(1, 2 * groups * 9, H, W, generator=g)).cuda()
     m = torch.sigmoid(torch.randn(1, groups * 9, H, W, generator=g)).cuda()
-    t_tv = timeit(lambda: tv.deform_conv2d(x, off, w, b, padding=(1, 1), mask=m))
-    t_me = timeit(lambda: ops.deform_conv2d(x, off, w, b, padding=(1, 1), mask=m))
-    nbytes = 4 * (x.numel() + off.numel() + m.numel() + Cout * H * W)
-    print(f"{name:30s} [{H}x{W}]: torchvision {t_tv*1e3:8.1f} us | b200vc {t_me*1e3:8.1f} us ({nbytes/t_me/1e6:5.0f} GB/s algorithmic) | x{t_tv/t_me:.1f}", flush=True)
+    nbytes = 4 * (x.numel() + 3 * m.numel() + Cout * H * W)
+    for kind in ("white-noise offsets (sigma 2 px)", "smooth offsets (upsampled x8, sigma 2 px)"):
+        if kind.startswith("white"):
+            off = (2.0 * torch.randn(1, 2 * groups * 9, H, W, generator=g)).cuda()
+        else:
+            off = torch.nn.functional.interpolate(2.0 * torch.randn(1, 2 * groups * 9, H // 8, W // 8, generator=g).cuda(),
+                                                  size=(H, W), mode="bilinear")
+        t_tv = timeit(lambda: tv.deform_conv2d(x, off, w, b, padding=(1, 1), mask=m))
+        t_me = timeit(lambda: ops.deform_conv2d(x, off, w, b, padding=(1, 1), mask=m))
+        t_nc = timeit(lambda: ops.deform_conv2d(x, off, w, b, padding=(1, 1), mask=m, use_workspace=False))
+        print(f"{name:28s} [{H}x{W}] {kind:42s}: torchvision {t_tv*1e3:7.1f} us | b200vc {t_me*1e3:7.1f} us "
+              f"({nbytes/t_me/1e6:5.0f} GB/s) x{t_tv/t_me:.1f} | NCHW kernel {t_nc*1e3:7.1f} us", flush=True)

@@ -28,7 +28,7 @@ _SIGNATURES = {
     "b200vc_warp2_half_sse_blocks": (c_int, [c_int, c_int]),
     "b200vc_warp2_half_sse_f32": (c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, c_int, c_int, c_int, c_int, c_void_p]),
     "b200vc_warp_sse_f32": (c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, c_int, c_int, c_int, c_int, c_void_p]),
-    "b200vc_deform_conv2d_f32": (c_int, [_fp, _fp, _fp, _fp, _fp, _fp] + [c_int] * 15 + [c_void_p]),
+    "b200vc_deform_conv2d_f32": (c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp] + [c_int] * 15 + [c_void_p]),
     "b200vc_spynet_pyramid_f32": (c_int, [_fp, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "b200vc_spynet_level_f32": (c_int, [_fp, c_int64, _fp, c_int64, _fp, _fp, _fp, _fp, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "b200vc_blend_residual_f32": (c_int, [c_int, _fp, _fp, c_int64, _fp, c_int64, _fp, _fp, _fp, _fp, c_int, c_int, c_int, c_int, c_void_p]),

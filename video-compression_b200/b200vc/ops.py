@@ -278,9 +278,11 @@ def warp_sse(img, flow, x_cur, variant="ac1", want_pred=False):
 
 
 # ------------------------------------------------------------------------- deformable convolution
-def deform_conv2d(input, offset, weight, bias=None, stride=(1, 1), padding=(0, 0), dilation=(1, 1), mask=None):
+def deform_conv2d(input, offset, weight, bias=None, stride=(1, 1), padding=(0, 0), dilation=(1, 1), mask=None,
+                  use_workspace=True):
     """``torchvision.ops.deform_conv2d`` (same signature and layouts; ICIP2023/src/model/m.py:29-34,
-    ICIP2024/src/model/helpers.py:40,57) without the im2col matrix."""
+    ICIP2024/src/model/helpers.py:40,57) without the im2col matrix.  ``use_workspace=False`` forces the NCHW gather
+    kernel (no scratch copy of the input)."""
     pair = lambda v: (int(v), int(v)) if isinstance(v, int) else (int(v[0]), int(v[1]))
     (sh, sw), (ph, pw), (dh, dw) = pair(stride), pair(padding), pair(dilation)
     x, off, w = _contig(input, "deform_conv2d(input)"), _contig(offset, "deform_conv2d(offset)"), \
@@ -316,8 +318,12 @@ def deform_conv2d(input, offset, weight, bias=None, stride=(1, 1), padding=(0, 0
     lib = _lib.load()
     p = lambda t: t.data_ptr() if t is not None else None
     nbytes = 4 * (x.numel() + off.numel() + (m.numel() if m is not None else 0) + out.numel())
+    cout_g = Cout // groups
+    fast = (use_workspace and cin_g in (4, 8, 12, 16) and cout_g in (4, 6, 8, 12, 16) and (Cin // og) % cin_g == 0
+            and K <= 9)
+    ws = torch.empty(x.numel(), device=x.device, dtype=x.dtype) if fast else None
     _run("deform_conv2d_f32", nbytes, lambda: lib.b200vc_deform_conv2d_f32(
-        x.data_ptr(), off.data_ptr(), p(m), w.data_ptr(), p(b), out.data_ptr(), N, Cin, H, W, Cout, kh, kw, sh, sw,
+        x.data_ptr(), off.data_ptr(), p(m), w.data_ptr(), p(b), out.data_ptr(), p(ws), N, Cin, H, W, Cout, kh, kw, sh, sw,
         ph, pw, dh, dw, groups, og, _stream()), tag=f"{N}x{Cin}->{Cout}x{H}x{W}g{groups}")
     return out
 
