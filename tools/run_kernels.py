@@ -13,7 +13,7 @@ import torch  # noqa: E402
 from b200vc import modules, ops  # noqa: E402
 from gpu_util import gc_case  # noqa: E402
 
-which = set(sys.argv[1:]) or {"gdn", "warp", "warp2", "blend", "gc", "eb"}
+which = set(sys.argv[1:]) or {"gdn", "warp", "warp2", "blend", "gc", "eb", "spynet", "sse", "dcn"}
 reps = int(os.environ.get("REPS", "1"))
 g = torch.Generator().manual_seed(0)
 N, H, W = 1, 1088, 1920
@@ -52,6 +52,31 @@ if "blend" in which:
     x = torch.rand(N, 3, H, W, device="cuda")
     for _ in range(reps):
         ops.blend_residual("mask", mask, both[:, :3], both[:, 3:], x)
+if "spynet" in which:
+    x1 = torch.rand(4, 3, H, W, generator=g).cuda()
+    x2 = torch.rand(4, 3, H, W, generator=g).cuda()
+    fl = torch.nn.functional.interpolate(2.0 * torch.randn(4, 2, 34, 60, generator=g), size=(H // 2, W // 2),
+                                         mode="bilinear").cuda()
+    for _ in range(reps):
+        p1, p2 = ops.spynet_pyramid(x1), ops.spynet_pyramid(x2)
+        ops.spynet_level(p1[-1], p2[-1], fl)          # TMA-staged (>= 2 Mpx per launch)
+        ops.spynet_level(p1[-2][:1], p2[-2][:1], fl[:1, :, ::2, ::2].contiguous())  # gather kernel
+if "sse" in which:
+    img = torch.rand(1, 3, 2160, 3840, generator=g).cuda()
+    cur = torch.rand(1, 3, 2160, 3840, generator=g).cuda()
+    f4k = torch.nn.functional.interpolate(3.0 * torch.randn(1, 2, 135, 240, generator=g), size=(2160, 3840),
+                                          mode="bilinear").cuda()
+    for _ in range(reps):
+        ops.warp_sse(img, f4k, cur, "ac1")
+if "dcn" in which:
+    Cin, Cout, h, w, groups = 128, 64, 544, 960, 16
+    xd = torch.randn(1, Cin, h, w, generator=g).cuda()
+    wd = (torch.randn(Cout, Cin // groups, 3, 3, generator=g) * 0.1).cuda()
+    od = torch.nn.functional.interpolate(2.0 * torch.randn(1, 2 * groups * 9, h // 8, w // 8, generator=g).cuda(),
+                                         size=(h, w), mode="bilinear")
+    md = torch.sigmoid(torch.randn(1, groups * 9, h, w, generator=g)).cuda()
+    for _ in range(reps):
+        ops.deform_conv2d(xd, od, wd, None, padding=(1, 1), mask=md)
 if "gc" in which:
     y, s, m = gc_case(3, 4, 128, 68, 120)
     for _ in range(reps):

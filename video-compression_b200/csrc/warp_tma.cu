@@ -47,7 +47,7 @@ __device__ __forceinline__ void up_ac(int dst, int in_size, float scale, int& i0
 }
 
 template <int VARIANT, bool SPY>
-__global__ void __launch_bounds__(kThreads, SPY ? 3 : 1)
+__global__ void __launch_bounds__(kThreads, SPY ? 3 : 0)
 warp_tma_kernel(const __grid_constant__ CUtensorMap map_img, const float* __restrict__ img,
                 const float* __restrict__ flow, const float* __restrict__ tab_x, const float* __restrict__ tab_y,
                 float* __restrict__ out, int64_t out_bs, WarpGeom g, SpyArgs spy) {
