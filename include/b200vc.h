@@ -151,6 +151,18 @@ B200VC_API int b200vc_deform_conv2d_f32(const float* input, const float* offset,
                                         int Cin, int H, int W, int Cout, int kh, int kw, int stride_h, int stride_w, int pad_h,
                                         int pad_w, int dil_h, int dil_w, int groups, int offset_groups, void* stream);
 
+/* ------------------------------------------------------- checkerboard context glue
+ * ICIP2024/src/model/compression_bottlenecks.py:237-268 (and :479-510, ICIP2023/src/model/elic.py).
+ * round_checker: y_hat = ste_round(y) = (round(y) - y) + y over the whole latent [N,C,H,W]; y_half = y_hat with the
+ *   anchor positions ((h + w) even: [0::2,0::2] and [1::2,1::2]) set to zero.  Either output may be NULL.
+ * checker_mask: dst = src with the positions of parity `zero_parity` ((h + w) & 1) set to zero; src / dst are
+ *   [N,C,H,W] blocks with batch strides (dst may be a channel slice of a concat buffer, or src itself).
+ *   The reference zeroes [0::2,1::2] and [1::2,0::2] of the context convolution's output: zero_parity = 1. */
+B200VC_API int b200vc_round_checker_f32(const float* y, float* y_hat, float* y_half, int N, int C, int H, int W,
+                                        void* stream);
+B200VC_API int b200vc_checker_mask_f32(const float* src, int64_t src_bs, float* dst, int64_t dst_bs, int N, int C, int H,
+                                       int W, int zero_parity, void* stream);
+
 /* ------------------------------------------------------------------------------------ blend / residual
  * Replaces LHBDC/model/m.py:63-67, Flex-Rate.../b_model/b_model.py:68-73, ICIP2024/src/opt_helpers.py:35-45.
  *   a, b: the two warped references [N,3,H,W] (batch strides a_bs, b_bs: may be halves of the concat

@@ -42,3 +42,37 @@ def get_best_down_ratio_prediction(model, xref1, xref2, scale1, scale2, xcur, le
             best_pred_psnr = psnr
             best_down_ratio = down_ratio
     return best_down_ratio, best_pred_psnr
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Checkerboard / channel-group context loop: ICIP2024/src/model/compression_bottlenecks.py:36-47 (ste_round) and
+# :229-269 (Offset_ELIC.forward; Res_ELIC :471-511 is the same loop), restated with the sub-modules passed in.
+def ste_round(x):
+    return (torch.round(x) - x).detach() + x
+
+
+def elic_context_likelihoods(y, hyper_params, context_prediction_models, channel_context_models, entropy_parameters,
+                             gaussian_conditional, inv_gain=None):
+    uneven_groups = [y[:, :6, :, :], y[:, 6:12, :, :], y[:, 12:24, :, :], y[:, 24:48, :, :], y[:, 48:, :, :]]
+    likelihoods_list = {}
+    for i, curr_y in enumerate(uneven_groups):
+        curr_y_hat = ste_round(curr_y)
+        y_half = curr_y_hat.clone()
+        y_half[:, :, 0::2, 0::2] = 0
+        y_half[:, :, 1::2, 1::2] = 0
+        ctx_params = context_prediction_models[i](y_half)
+        ctx_params[:, :, 0::2, 1::2] = 0
+        ctx_params[:, :, 1::2, 0::2] = 0
+        if i == 0:
+            gaussian_params = entropy_parameters[i](torch.cat((ctx_params, hyper_params), dim=1))
+        else:
+            channel_context_in = ste_round(torch.cat(uneven_groups[:i], dim=1))
+            channel_context = channel_context_models[i - 1](channel_context_in)
+            gaussian_params = entropy_parameters[i](torch.cat((ctx_params, channel_context, hyper_params), dim=1))
+        scales_hat, means_hat = gaussian_params.chunk(2, 1)
+        _, y_likelihoods = gaussian_conditional(curr_y, scales_hat, means=means_hat)
+        likelihoods_list[f"y_{i}"] = y_likelihoods
+    y_hat = ste_round(y)
+    if inv_gain is not None:
+        y_hat = y_hat * inv_gain.unsqueeze(0).unsqueeze(2).unsqueeze(3)
+    return likelihoods_list, y_hat

@@ -29,6 +29,8 @@ _SIGNATURES = {
     "b200vc_warp2_half_sse_f32": (c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, c_int, c_int, c_int, c_int, c_void_p]),
     "b200vc_warp_sse_f32": (c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, c_int, c_int, c_int, c_int, c_void_p]),
     "b200vc_deform_conv2d_f32": (c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp] + [c_int] * 15 + [c_void_p]),
+    "b200vc_round_checker_f32": (c_int, [_fp, _fp, _fp, c_int, c_int, c_int, c_int, c_void_p]),
+    "b200vc_checker_mask_f32": (c_int, [_fp, c_int64, _fp, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "b200vc_spynet_pyramid_f32": (c_int, [_fp, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "b200vc_spynet_level_f32": (c_int, [_fp, c_int64, _fp, c_int64, _fp, _fp, _fp, _fp, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "b200vc_blend_residual_f32": (c_int, [c_int, _fp, _fp, c_int64, _fp, c_int64, _fp, _fp, _fp, _fp, c_int, c_int, c_int, c_int, c_void_p]),

@@ -118,3 +118,48 @@ class OffsetDiversity(nn.Module):
 
     def warp(self, img, flow):
         return ops.backwarp(img, flow, "ac1")
+
+
+# ------------------------------------------------------------------------- checkerboard context loop
+ELIC_GROUPS = (6, 6, 12, 24, None)  # compression_bottlenecks.py:229-235: channel groups, the last one takes the rest
+
+
+def elic_context_likelihoods(y, hyper_params, context_prediction_models, channel_context_models, entropy_parameters,
+                             gaussian_conditional, group_sizes=ELIC_GROUPS, inv_gain=None):
+    """The channel-group x checkerboard entropy loop of ``Offset_ELIC`` / ``Res_ELIC``
+    (ICIP2024/src/model/compression_bottlenecks.py:229-269, :471-511) with the reference's own sub-modules.
+
+    Returns ``({"y_0": lik, ...}, y_hat)`` where ``y_hat = ste_round(y) * inv_gain`` (``inv_gain`` [M] or None).
+    The latent is quantised ONCE (K-CHK ``round_checker``: rounded + anchor-zeroed copies; every group and every
+    "earlier groups" context input is a channel slice of those), the context convolution's output is checkerboard-
+    masked straight into the entropy-parameter network's input buffer (``checker_mask``), and the likelihoods come
+    from ``gaussian_conditional`` (the K-GC kernel when the module is the b200vc mirror or was ``patch()``-ed)."""
+    N, M, H, W = y.shape
+    sizes, start = [], 0
+    for s in group_sizes:
+        s = M - start if s is None else s
+        sizes.append((start, start + s))
+        start += s
+    if start != M:
+        raise ValueError(f"channel groups {group_sizes} do not cover {M} channels")
+    y_hat, y_half = ops.round_checker(y)
+    likelihoods = {}
+    for i, (a, b) in enumerate(sizes):
+        ctx = context_prediction_models[i](y_half[:, a:b])
+        parts = [ctx.shape[1]]
+        chan = None
+        if i > 0:
+            chan = channel_context_models[i - 1](y_hat[:, :a])       # == ste_round(cat(groups[:i]))
+            parts.append(chan.shape[1])
+        parts.append(hyper_params.shape[1])
+        buf = torch.empty((N, sum(parts), H, W), device=y.device, dtype=y.dtype)
+        ops.checker_mask(ctx, out=buf[:, :parts[0]], zero_parity=1)
+        if chan is not None:
+            buf[:, parts[0]:parts[0] + parts[1]] = chan
+        buf[:, -parts[-1]:] = hyper_params
+        scales_hat, means_hat = entropy_parameters[i](buf).chunk(2, 1)
+        _, lik = gaussian_conditional(y[:, a:b], scales_hat, means=means_hat)
+        likelihoods[f"y_{i}"] = lik
+    if inv_gain is not None:
+        y_hat = y_hat * inv_gain.view(1, -1, 1, 1)
+    return likelihoods, y_hat

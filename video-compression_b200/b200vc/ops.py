@@ -277,6 +277,42 @@ def warp_sse(img, flow, x_cur, variant="ac1", want_pred=False):
     return sum_partials(part, nb, N), pred
 
 
+# --------------------------------------------------------------------- checkerboard context glue
+def round_checker(y, want_half=True):
+    """``ste_round(y)`` and its anchor-zeroed copy (compression_bottlenecks.py:238-242) for the whole latent at once.
+    Returns (y_hat, y_half or None)."""
+    y = _contig(y, "round_checker(y)")
+    if y.dim() != 4:
+        raise RuntimeError(f"round_checker: expected [N,C,H,W], got {tuple(y.shape)}")
+    N, C, H, W = y.shape
+    y_hat = torch.empty_like(y)
+    y_half = torch.empty_like(y) if want_half else None
+    if y.numel() == 0:
+        return y_hat, y_half
+    lib = _lib.load()
+    _run("round_checker_f32", 4 * y.numel() * (2 + int(want_half)), lambda: lib.b200vc_round_checker_f32(
+        y.data_ptr(), y_hat.data_ptr(), y_half.data_ptr() if want_half else None, N, C, H, W, _stream()))
+    return y_hat, y_half
+
+
+def checker_mask(src, out=None, zero_parity=1):
+    """``x[:, :, 0::2, 1::2] = 0; x[:, :, 1::2, 0::2] = 0`` (zero_parity=1; compression_bottlenecks.py:245-246) as one
+    pass; ``out`` may be a channel slice of a concat buffer, or ``src`` itself."""
+    src, sp, sbs = _planes(src, "checker_mask(src)")
+    N, C, H, W = src.shape
+    if out is None:
+        out = torch.empty_like(src)
+    o, op, obs = _planes(out, "checker_mask(out)")
+    if o is not out or tuple(out.shape) != (N, C, H, W):
+        raise RuntimeError("checker_mask: `out` must be a dense [N,C,H,W] block (channel slices are fine)")
+    if src.numel() == 0:
+        return out
+    lib = _lib.load()
+    _run("checker_mask_f32", 8 * src.numel(), lambda: lib.b200vc_checker_mask_f32(
+        sp, sbs, op, obs, N, C, H, W, int(zero_parity), _stream()))
+    return out
+
+
 # ------------------------------------------------------------------------- deformable convolution
 def deform_conv2d(input, offset, weight, bias=None, stride=(1, 1), padding=(0, 0), dilation=(1, 1), mask=None,
                   use_workspace=True):
