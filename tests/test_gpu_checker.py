@@ -58,7 +58,7 @@ def _modules(M, N, seed):
     chan = nn.ModuleList(nn.Sequential(conv5(c, N), nn.ReLU(inplace=True), conv5(N, 2 * M)) for c in [6, 12, 24, 48])
     ent = nn.ModuleList(nn.Sequential(nn.Conv2d(i, M, 1), nn.LeakyReLU(inplace=True), nn.Conv2d(M, 2 * o, 1))
                         for i, o in zip([4 * M] + [6 * M] * 4, groups))
-    return ctx.cuda(), chan.cuda(), ent.cuda()
+    return ctx.cuda().eval(), chan.cuda().eval(), ent.cuda().eval()
 
 
 @pytest.mark.parametrize("N", [1, 2])
@@ -70,8 +70,8 @@ def test_context_loop_matches_reference_restatement(N, strict_fp32):
     y = (3.0 * torch.randn(N, M, H, W, generator=g)).cuda()
     hyper = torch.randn(N, 2 * M, H, W, generator=g).cuda()
     inv_gain = (1.0 + 0.1 * torch.randn(M, generator=g)).abs().cuda()
-    gc_o = cai.GaussianConditional(None).cuda()
-    gc_p = modules.GaussianConditional(None).cuda()
+    gc_o = cai.GaussianConditional(None).cuda().eval()
+    gc_p = modules.GaussianConditional(None).cuda().eval()
     with torch.no_grad():
         want, y_hat_o = o_icip.elic_context_likelihoods(y, hyper, ctx, chan, ent, gc_o, inv_gain)
         before = icip.ops.launch_count()
