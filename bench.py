@@ -202,7 +202,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -361,7 +361,7 @@ def run_product(args):
         if W_ == 1 and not args.no_cpu_baseline:
             v, cores, sample, _ = cpu_reference_frames_per_s(args, 1, 0, 120.0)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
-        print(json.dumps(line), flush=True)
+        emit(line)
     bd.barrier()
     if torch.distributed.is_initialized():
         torch.distributed.destroy_process_group()
@@ -389,6 +389,29 @@ def load_traffic_note(kernel):
         return None
 
 
+_RESULT_FD = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's real stdout; everything else any library prints (NCCL's version
+    banner, cuDNN / torch warnings) was redirected to stderr by `claim_stdout`."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
+def claim_stdout():
+    """Keep fd 1 for the result line only: duplicate it, then point fd 1 (C and Python level) at stderr."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
 if __name__ == "__main__":
     a = parse()
+    claim_stdout()
     sys.exit(run_reference(a) if a.impl == "reference" else run_product(a))
