@@ -239,7 +239,8 @@ B200VC_API int b200vc_sum_partials_f64(const double* partials, int n_per, int n_
 
 /* -------------------------------------------------------------------------------------------- metrics
  * Replaces the D2H + numpy PSNR of LHBDC/test/testing.py:176-182: sum over the unpadded crop [:h,:w] of
- * (round(clip(a)*255) - round(clip(b)*255))^2, as n_blocks per-CTA double partials (exact integers).
+ * (round(clip(a)*255) - round(clip(b)*255))^2 PER SAMPLE, as partials[N][n_blocks] per-CTA doubles (exact integers;
+ * reduce with b200vc_sum_partials_f64(partials, n_blocks, N, out)).
  */
 B200VC_API int b200vc_sse_u8_f32(const float* a, const float* b, double* partials, int n_blocks, int N, int C,
                       int H, int W, int h, int w, void* stream);

@@ -58,3 +58,9 @@ def test_sse_u8_matches_the_numpy_psnr_path():
     assert got.item() == want
     mse = want / ua.size
     assert abs(gop.psnr_from_sse(got, ua.size).item() - 10 * np.log10(255.0 ** 2 / mse)) < 1e-9
+    # per-sample sums for a batch: frame 0 as above, frame 1 = its operands swapped and shifted
+    a2, b2 = torch.cat([a, b.roll(3, 3)], 0), torch.cat([b, a], 0)
+    got2 = ops.sse_u8(a2, b2, h, w)
+    to_u8n = lambda t, n: np.round(np.clip(t[n, :, :h, :w].cpu().numpy(), 0, 1) * 255.).astype(np.float64)
+    want2 = [((to_u8n(a2, n) - to_u8n(b2, n)) ** 2).sum() for n in range(2)]
+    assert got2.shape == (2,) and got2[0].item() == want2[0] == want and got2[1].item() == want2[1]

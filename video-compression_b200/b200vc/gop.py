@@ -113,12 +113,12 @@ class GopCoder:
             else:
                 n, l = self.level_quality[level]
                 x_hat, b = self.model.forward_device(xb, xc, xa, [n], l)[:2]
+            level_sse = ops.sse_u8(x_hat, xc, h, w)   # one launch scores every frame of the level
             for k, f in enumerate(level_frames):
                 sl = slice(k * G, (k + 1) * G)
                 decoded[f] = x_hat[sl]
                 bits[:, f] = b[sl]
-                for gi in range(G):
-                    sse[gi, f] = ops.sse_u8(x_hat[k * G + gi:k * G + gi + 1], frames[gi:gi + 1, f], h, w)[0]
+                sse[:, f] = level_sse[sl]
         if want_decoded:
             return bits, sse, torch.stack([decoded[t] for t in range(T)], 1)
         return bits, sse

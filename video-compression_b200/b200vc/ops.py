@@ -412,18 +412,18 @@ def blend_residual(mode, mask, a, b, x_cur, want_pred=True, want_res=True, want_
 
 def sse_u8(a, b, h, w):
     """Sum over the crop [:h,:w] of (uint8(a) - uint8(b))^2 with float_to_uint8 = round(clip(x,0,1)*255)
-    (LHBDC/test/testing.py:176-182); returns a 1-element float64 device tensor (exact integer)."""
+    (LHBDC/test/testing.py:176-182); returns a float64 device tensor [N] of per-sample sums (exact integers)."""
     a = _contig(a, "sse_u8(a)")
     b = _contig(b, "sse_u8(b)")
     if a.shape != b.shape or a.dim() != 4:
         raise RuntimeError("sse_u8: a and b must be NCHW tensors of the same shape")
     N, C, H, W = a.shape
-    nb = reduce_blocks(N * C * h * w)
-    part = torch.empty(nb, device=a.device, dtype=torch.float64)
+    nb = reduce_blocks(C * h * w)
+    part = torch.empty(N * nb, device=a.device, dtype=torch.float64)
     lib = _lib.load()
     _run("sse_u8_f32", 8 * N * C * h * w, lambda: lib.b200vc_sse_u8_f32(
         a.data_ptr(), b.data_ptr(), part.data_ptr(), nb, N, C, H, W, h, w, _stream()))
-    return sum_partials(part, nb, 1)
+    return sum_partials(part, nb, N)
 
 
 # --------------------------------------------------------------------------------------- GDN

@@ -100,8 +100,11 @@ __device__ __forceinline__ float sq_u8_diff(float a, float b) {
 }
 
 __global__ void __launch_bounds__(kBlendThreads)
-sse_u8_kernel(const float* __restrict__ a, const float* __restrict__ b, double* __restrict__ partials,
+sse_u8_kernel(const float* __restrict__ a0, const float* __restrict__ b0, double* __restrict__ partials,
               int planes, int H, int W, int h, int w) {
+  // blockIdx.y = sample: per-sample sums, so one launch scores all frames of a hierarchy level
+  const float* a = a0 + (int64_t)blockIdx.y * planes * H * W;
+  const float* b = b0 + (int64_t)blockIdx.y * planes * H * W;
   const int rows = planes * h;
   const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15u) == 0;
   const int w4 = vec ? (w / 4) : 0;
@@ -129,7 +132,7 @@ sse_u8_kernel(const float* __restrict__ a, const float* __restrict__ b, double* 
   if (threadIdx.x == 0) {
     double tot = 0.0;
     for (int i = 0; i < kBlendThreads / 32; ++i) tot += s_part[i];
-    partials[blockIdx.x] = tot;
+    partials[(int64_t)blockIdx.y * gridDim.x + blockIdx.x] = tot;
   }
 }
 
@@ -182,7 +185,8 @@ extern "C" int b200vc_sse_u8_f32(const float* a, const float* b, double* partial
   B200VC_REQUIRE(a && b && partials, "sse_u8_f32: null pointer");
   B200VC_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && h > 0 && w > 0 && h <= H && w <= W && n_blocks > 0,
                  "sse_u8_f32: bad shape");
-  sse_u8_kernel<<<n_blocks, kBlendThreads, 0, (cudaStream_t)stream>>>(a, b, partials, N * C, H, W, h, w);
+  B200VC_REQUIRE(N <= 65535, "sse_u8_f32: N too large");
+  sse_u8_kernel<<<dim3(n_blocks, N), kBlendThreads, 0, (cudaStream_t)stream>>>(a, b, partials, C, H, W, h, w);
   return check_launch("sse_u8_f32");
 }
 
