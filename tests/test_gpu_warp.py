@@ -32,7 +32,7 @@ def test_warp_matches_reference_golden(golden_dir, variant, tag):
 
 @pytest.mark.parametrize("variant", ["lhbdc", "flex", "ac1"])
 @pytest.mark.parametrize("shape", [(1, 3, 64, 96), (2, 3, 37, 53), (1, 1, 8, 8), (3, 2, 16, 12), (1, 64, 68, 120),
-                                   (1, 3, 1, 40), (1, 3, 40, 1)])
+                                   (2, 13, 40, 52), (1, 96, 34, 60), (1, 3, 1, 40), (1, 3, 40, 1)])
 def test_warp_matches_oracle_on_device(variant, shape):
     from b200vc import ops
     if variant != "flex" and 1 in shape[2:]:

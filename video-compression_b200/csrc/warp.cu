@@ -86,6 +86,40 @@ warp_kernel(const float* __restrict__ img, int64_t img_bs, const float* __restri
   }
 }
 
+// Many-channel form (ICIP feature warps, SURVEY 8a W4: [1,64,544,960], [1,96,272,480], [1,128,136,240]): the channel
+// loop of the generic kernel is a serial chain of C gathers per thread and leaves small planes with fewer CTAs than
+// SMs.  Here grid.z = sample x channel chunk and a thread owns one pixel of CC channels: all 4*CC taps in flight, the
+// coordinate chain (cheap next to 4*CC gathers) recomputed per chunk.
+template <int VARIANT, int CC>
+__global__ void __launch_bounds__(kWarpThreads)
+warp_mc_kernel(const float* __restrict__ img, int64_t img_bs, const float* __restrict__ flow,
+               const float* __restrict__ tab_x, const float* __restrict__ tab_y, float* __restrict__ out,
+               int64_t out_bs, int C, int chunks, WarpGeom g) {
+  constexpr bool BORDER = (VARIANT != B200VC_WARP_FLEX);
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * (kWarpThreads / 32) + (threadIdx.x >> 5);
+  const int n = blockIdx.z / chunks, c0 = (blockIdx.z % chunks) * CC;
+  if (x >= g.W || y >= g.H) return;
+  const int HW = g.H * g.W;
+  const int o = y * g.W + x;
+  const float* f = flow + (int64_t)n * 2 * HW + o;
+  float ix, iy;
+  coords<VARIANT, true>(g, x, y, __ldg(f), __ldg(f + HW), BORDER ? __ldg(tab_x + x) : 0.f,
+                        BORDER ? __ldg(tab_y + y) : 0.f, ix, iy);
+  const Taps t = make_taps<BORDER>(ix, iy, g.H, g.W);
+  const float* ip = img + (int64_t)n * img_bs + (int64_t)c0 * HW;
+  float* op = out + (int64_t)n * out_bs + (int64_t)c0 * HW + o;
+  float r[CC];
+  if (c0 + CC <= C) {
+#pragma unroll
+    for (int c = 0; c < CC; ++c) r[c] = sample<BORDER>(ip + (int64_t)c * HW, t);
+#pragma unroll
+    for (int c = 0; c < CC; ++c) op[(int64_t)c * HW] = r[c];
+  } else {
+    for (int c = 0; c0 + c < C; ++c) op[(int64_t)c * HW] = sample<BORDER>(ip + (int64_t)c * HW, t);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // warp2: LHBDC flow glue + two warps + concat in one pass.
 // ATen upsample_bilinear2d (align_corners=False, scale_factor=4 => rscale = 0.25):
@@ -290,7 +324,22 @@ extern "C" int b200vc_warp_f32(const float* img, int64_t img_bs, const float* fl
       case 2: B200VC_WARP_LAUNCH(2); break;
       case 3: B200VC_WARP_LAUNCH(3); break;
       case 4: B200VC_WARP_LAUNCH(4); break;
-      default: B200VC_WARP_LAUNCH_PX(0, 1); break;
+      default: {
+        constexpr int CC = 8;
+        const int chunks = (C + CC - 1) / CC;
+        if ((int64_t)N * chunks <= 65535) {
+          const dim3 gmc((W + 31) / 32, (H + rows - 1) / rows, N * chunks);
+          if (variant == B200VC_WARP_LHBDC)
+            warp_mc_kernel<0, CC><<<gmc, kWarpThreads, 0, st>>>(img, img_bs, flow, tab_x, tab_y, out, out_bs, C, chunks, g);
+          else if (variant == B200VC_WARP_FLEX)
+            warp_mc_kernel<1, CC><<<gmc, kWarpThreads, 0, st>>>(img, img_bs, flow, tab_x, tab_y, out, out_bs, C, chunks, g);
+          else
+            warp_mc_kernel<2, CC><<<gmc, kWarpThreads, 0, st>>>(img, img_bs, flow, tab_x, tab_y, out, out_bs, C, chunks, g);
+        } else {
+          B200VC_WARP_LAUNCH_PX(0, 1);
+        }
+        break;
+      }
     }
   }
 #undef B200VC_WARP_LAUNCH
