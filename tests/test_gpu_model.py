@@ -144,3 +144,27 @@ def test_gop_coder_batches_levels_and_is_deterministic(models):
     with torch.no_grad():
         _, b4, _ = prod.forward_device(gops[1:2, 0], gops[1:2, 4], gops[1:2, 8])
     assert abs(b4.item() - bits[1, 4].item()) / b4.item() < 1e-4
+
+
+def test_forward_device_is_cuda_graph_capturable(models, triple):
+    """the library never allocates, synchronises or keeps mutable state, so the whole B-frame step can
+    be captured once and replayed on new frames (tensor maps and workspaces are baked in at capture time)."""
+    _, prod = models
+    _, (xb, xc, xa) = triple
+    sb, sc, sa = xb.clone(), xc.clone(), xa.clone()
+    with torch.no_grad():
+        for _ in range(2):                                   # warm-up: lazy tables, cuDNN plans
+            prod.forward_device(sb, sc, sa)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            x_hat, bits, _ = prod.forward_device(sb, sc, sa)
+        # replay on different frames: swap the two references
+        sb.copy_(xa)
+        sa.copy_(xb)
+        graph.replay()
+        torch.cuda.synchronize()
+        got_x, got_bits = x_hat.clone(), bits.clone()
+        want_x, want_bits, _ = prod.forward_device(xa, xc, xb)
+    assert torch.equal(got_bits, want_bits)
+    assert torch.equal(got_x, want_x)
