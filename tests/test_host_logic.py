@@ -116,3 +116,45 @@ def test_flexrate_mirror_checkpoint_layout_and_gains():
         assert torch.equal(gp.gain(n, l), go.gain(n, l)) and gp.gain(n, l).shape == (1, 128)
     with pytest.raises(RuntimeError, match="CUDA tensor"):
         prod.flow_compressor.compress(torch.rand(1, 19, 64, 64), [0], 1.0)
+
+
+def _reference_literals(path, names):
+    """Top-level literal assignments of a reference script, evaluated with ast.literal_eval (no code is executed)."""
+    import ast
+    import os
+    if not os.path.exists(path):
+        pytest.skip("/root/reference is not mounted here")
+    out = {}
+    for node in ast.parse(open(path).read()).body:
+        if isinstance(node, ast.Assign) and len(node.targets) == 1 and isinstance(node.targets[0], ast.Name) \
+                and node.targets[0].id in names:
+            out[node.targets[0].id] = ast.literal_eval(node.value)
+    return out
+
+
+def test_schedules_and_qualities_equal_the_reference_scripts():
+    """gop.py's tables against the literals in the reference's own drivers (LHBDC/test/testing.py:70-74,
+    Flex-Rate.../test/testing.py:71-89)."""
+    ref = _reference_literals("/root/reference/Flex-Rate-Hier-Bidir-Video-Compression/test/testing.py",
+                              {"coding_order", "decoding_info", "hier_levels", "qualities"})
+    sch = gop.FLEX_GOP16
+    assert {k: tuple(v) for k, v in ref["decoding_info"].items()} == sch.refs
+    assert ref["hier_levels"] == sch.levels
+    assert sorted(ref["coding_order"][2:]) == sorted(sch.refs)
+    assert tuple((q, {k: tuple(v) for k, v in d.items()}) for q, d in ref["qualities"]) == gop.FLEX_QUALITIES
+    ref8 = _reference_literals("/root/reference/LHBDC/test/testing.py", {"coding_order", "decoding_info", "hier_levels"})
+    if {"decoding_info", "hier_levels"} <= set(ref8):
+        assert {k: tuple(v) for k, v in ref8["decoding_info"].items()} == gop.LHBDC_GOP8.refs
+        assert ref8["hier_levels"] == gop.LHBDC_GOP8.levels
+
+
+def test_ojsp_ratio_table_equals_the_reference():
+    import ast
+    import os
+    import re
+    path = "/root/reference/OJSP2025/video_model.py"
+    if not os.path.exists(path):
+        pytest.skip("/root/reference is not mounted here")
+    from b200vc import ojsp
+    m = re.search(r"downsampling_ratios\s*=\s*(\[[^\]]*\])", open(path).read())
+    assert m and tuple(float(v) for v in ast.literal_eval(m.group(1))) == ojsp.DOWNSAMPLING_RATIOS

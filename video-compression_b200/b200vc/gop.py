@@ -51,7 +51,7 @@ FLEX_QUALITIES = (
     (5, {0: (1, 1.), 1: (0, 0.33), 2: (0, 0.66), 3: (0, 1.)}), (6, {0: (1, 0.66), 1: (1, 1.), 2: (0, 0.33), 3: (0, 0.66)}),
     (6, {0: (1, 0.33), 1: (1, 0.66), 2: (1, 1.), 3: (0, 0.33)}), (6, {0: (2, 1.), 1: (1, 0.33), 2: (1, 0.66), 3: (1, 1.)}),
     (7, {0: (2, 0.66), 1: (2, 1.), 2: (1, 0.33), 3: (1, 0.66)}), (7, {0: (2, 0.33), 1: (2, 0.66), 2: (2, 1.), 3: (1, 0.33)}),
-    (7, {0: (3, 1.), 1: (2, 0.33), 2: (2, 0.66), 3: (2, 1.)}), (8, {0: (3, 1.), 1: (3, 1.), 2: (2, 0.33), 3: (2, 0.66)}),
+    (7, {0: (3, 1.), 1: (2, 0.33), 2: (2, 0.66), 3: (2, 1.)}), (8, {0: (3, 1.), 1: (3, 1.), 2: (3, 1.), 3: (2, 0.33)}),
 )
 
 
