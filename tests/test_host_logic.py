@@ -158,3 +158,27 @@ def test_ojsp_ratio_table_equals_the_reference():
     from b200vc import ojsp
     m = re.search(r"downsampling_ratios\s*=\s*(\[[^\]]*\])", open(path).read())
     assert m and tuple(float(v) for v in ast.literal_eval(m.group(1))) == ojsp.DOWNSAMPLING_RATIOS
+
+
+def test_icip_constants_equal_the_reference():
+    import os
+    import re
+    base = "/root/reference"
+    if not os.path.exists(base):
+        pytest.skip("/root/reference is not mounted here")
+    from b200vc import icip, modules
+    src = open(f"{base}/ICIP2024/src/opt_helpers.py").read()
+    m = re.search(r"for down_ratio in \[([^\]]*)\]", src)
+    assert m and tuple(int(v) for v in m.group(1).split(",")) == icip.DOWN_RATIOS
+    elic = open(f"{base}/ICIP2023/src/model/elic.py").read()
+    consts = {k: float(re.search(rf"^{k}\s*=\s*([0-9.]+)", elic, re.M).group(1))
+              for k in ("SCALES_MIN", "SCALES_MAX", "SCALES_LEVELS")}
+    assert (consts["SCALES_MIN"], consts["SCALES_MAX"], int(consts["SCALES_LEVELS"])) == \
+        (modules.SCALES_MIN, modules.SCALES_MAX, modules.SCALES_LEVELS)
+    cb = open(f"{base}/ICIP2024/src/model/compression_bottlenecks.py").read()
+    groups = re.search(r"uneven_groups = \[(.*?)\]\n", cb, re.S).group(1)
+    bounds = [int(v) for v in re.findall(r"y\[:, (?::)?(\d+)", groups)]
+    # y[:, :6], y[:, 6:12], y[:, 12:24], y[:, 24:48], y[:, 48:]  ->  group sizes 6, 6, 12, 24, rest
+    starts = sorted(set(bounds))
+    sizes = tuple(b - a for a, b in zip([0] + starts[:-1], starts))
+    assert sizes + (None,) == icip.ELIC_GROUPS
