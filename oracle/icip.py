@@ -76,3 +76,22 @@ def elic_context_likelihoods(y, hyper_params, context_prediction_models, channel
     if inv_gain is not None:
         y_hat = y_hat * inv_gain.unsqueeze(0).unsqueeze(2).unsqueeze(3)
     return likelihoods_list, y_hat
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# ICIP2024/src/model/helpers.py:35-59 (OffsetDiversity.prep / forward) restated on oracle.deform; pinned against the
+# reference's own class run on torchvision (oracle/make_golden_icip.py -> tests/golden/icip_reference.npz).
+def offset_diversity_prep(out, flow, magnitude):
+    o1, o2, mask = torch.chunk(out, 3, dim=1)
+    mask = torch.sigmoid(mask)
+    offset = torch.tanh(torch.cat((o1, o2), dim=1)) * magnitude
+    offset = offset + flow.flip(1).repeat(1, offset.size(1) // 2, 1, 1)
+    return offset, mask
+
+
+def offset_diversity_forward(weight, bias, magnitude, x1, offset1, flow1, x2, offset2, flow2):
+    from .deform import deform_conv2d
+    offset1, mask1 = offset_diversity_prep(offset1, flow1, magnitude)
+    offset2, mask2 = offset_diversity_prep(offset2, flow2, magnitude)
+    return deform_conv2d(torch.cat((x1, x2), dim=1), torch.cat((offset1, offset2), dim=1), weight, bias,
+                         padding=(1, 1), mask=torch.cat((mask1, mask2), dim=1))

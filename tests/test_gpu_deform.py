@@ -123,3 +123,21 @@ def test_bad_shapes_raise():
         ops.deform_conv2d(x, off, w, b, mask=m[:, :-1], **kw)
     with pytest.raises(RuntimeError):
         ops.deform_conv2d(x.cpu(), off, w, b, mask=m, **kw)
+
+
+def test_offset_diversity_matches_the_reference_golden(golden_dir):
+    """vs the reference's own ``OffsetDiversity`` class run on torchvision (tests/golden/icip_reference.npz)."""
+    import os
+
+    import numpy as np
+    from b200vc import icip, ops
+    g = np.load(os.path.join(golden_dir, "icip_reference.npz"))
+    t = lambda k: torch.from_numpy(g[k]).cuda()
+    mod = icip.OffsetDiversity(16, 10.0).cuda().eval()
+    mod.fusion.load_state_dict({"weight": t("weight"), "bias": t("bias")})
+    with torch.no_grad():
+        out = mod(t("x1"), t("o1"), t("f1"), t("x2"), t("o2"), t("f2"))
+    assert (out - t("out")).abs().max().item() < 2e-5 * max(1.0, t("out").abs().max().item())
+    assert (mod.warp(t("x1"), t("f1")) - t("warped")).abs().max().item() < 2e-5
+    y_hat, _ = ops.round_checker(t("ste_in").view(1, 1, 8, 8))
+    assert torch.equal(y_hat.view(-1), t("ste_out"))

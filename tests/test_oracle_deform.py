@@ -36,3 +36,22 @@ def test_oracle_matches_torchvision_cpu(case):
     assert got.shape == want.shape
     err = (got - want).abs().max().item()
     assert err < 2e-5 * max(1.0, want.abs().max().item()), err
+
+
+def test_offset_diversity_and_ste_round_match_the_reference_classes():
+    """Golden vectors produced by the reference's own ``OffsetDiversity`` (ICIP2024/src/model/helpers.py:35-69, on
+    torchvision) and ``ste_round`` (compression_bottlenecks.py:36-47): oracle/make_golden_icip.py."""
+    import os
+
+    import numpy as np
+
+    from oracle import icip as o_icip
+    from oracle import warp as o_warp
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "icip_reference.npz"))
+    t = lambda k: torch.from_numpy(g[k])
+    off1, m1 = o_icip.offset_diversity_prep(t("o1"), t("f1"), 10.0)
+    assert torch.equal(off1, t("off1")) and torch.equal(m1, t("m1"))
+    out = o_icip.offset_diversity_forward(t("weight"), t("bias"), 10.0, t("x1"), t("o1"), t("f1"), t("x2"), t("o2"), t("f2"))
+    assert (out - t("out")).abs().max().item() < 2e-5 * max(1.0, t("out").abs().max().item())
+    assert torch.equal(o_icip.ste_round(t("ste_in")), t("ste_out"))
+    assert torch.equal(o_warp.warp_ac1(t("x1"), t("f1")), t("warped"))
