@@ -262,7 +262,7 @@ gdn_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
       mbar_init(d_full(d), 1);
       mbar_init(d_empty(d), kEpiWarps);
     }
-    mbar_init(gamma_ready, kEpiWarps);
+    mbar_init(gamma_ready, kXfWarps + kEpiWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_out)) : "memory");
@@ -279,14 +279,16 @@ gdn_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  // gamma hi/lo -> TMEM (lane = output channel i, column = input channel j), by the epilogue warps:
-  // warp w owns lane quarter (w & 3); the two warps of a quarter take hi and lo respectively.
-  if (warp >= kFirstEpi) {
-    const int q = warp & 3, which = (warp - kFirstEpi) >> 2;
+  // gamma hi/lo -> TMEM (lane = output channel i, column = input channel j), by the 16 split + epilogue warps (all
+  // idle until the first tile lands): warp w owns lane quarter (w & 3); the four warps of a quarter take
+  // {hi, lo} x {columns 0-63, 64-127}: two dependent L2 round trips per warp instead of four.
+  if (warp >= kFirstXf) {
+    const int q = warp & 3, grp = (warp - kFirstXf) >> 2;   // kFirstXf = 2: warps 2..17 -> groups 0..3
+    const int which = grp & 1, half = grp >> 1;
     const int i = 32 * q + lane;
     const float* src_row = params + kC + 2 * kC * kC + (int64_t)which * kC * kC + (int64_t)i * kC;
 #pragma unroll 1
-    for (int part = 0; part < 4; ++part) {
+    for (int part = 2 * half; part < 2 * half + 2; ++part) {
       uint32_t v[32];
 #pragma unroll
       for (int e = 0; e < 32; e += 4) {
