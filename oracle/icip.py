@@ -53,29 +53,33 @@ def ste_round(x):
 
 def elic_context_likelihoods(y, hyper_params, context_prediction_models, channel_context_models, entropy_parameters,
                              gaussian_conditional, inv_gain=None):
-    uneven_groups = [y[:, :6, :, :], y[:, 6:12, :, :], y[:, 12:24, :, :], y[:, 24:48, :, :], y[:, 48:, :, :]]
-    likelihoods_list = {}
-    for i, curr_y in enumerate(uneven_groups):
-        curr_y_hat = ste_round(curr_y)
-        y_half = curr_y_hat.clone()
-        y_half[:, :, 0::2, 0::2] = 0
-        y_half[:, :, 1::2, 1::2] = 0
-        ctx_params = context_prediction_models[i](y_half)
-        ctx_params[:, :, 0::2, 1::2] = 0
-        ctx_params[:, :, 1::2, 0::2] = 0
-        if i == 0:
-            gaussian_params = entropy_parameters[i](torch.cat((ctx_params, hyper_params), dim=1))
-        else:
-            channel_context_in = ste_round(torch.cat(uneven_groups[:i], dim=1))
-            channel_context = channel_context_models[i - 1](channel_context_in)
-            gaussian_params = entropy_parameters[i](torch.cat((ctx_params, channel_context, hyper_params), dim=1))
-        scales_hat, means_hat = gaussian_params.chunk(2, 1)
-        _, y_likelihoods = gaussian_conditional(curr_y, scales_hat, means=means_hat)
-        likelihoods_list[f"y_{i}"] = y_likelihoods
+    """Plain-torch statement of the channel-group / checkerboard entropy loop (reference lines cited above).
+    Group g covers channels [lo_g, hi_g) with sizes 6, 6, 12, 24, rest.  For each group:
+      1. quantise the group, blank its anchor sites ((row + col) even) and run the group's context conv;
+      2. blank the non-anchor sites ((row + col) odd) of the conv output;
+      3. the parameter net sees [that | channel context of all earlier quantised groups (absent for g = 0) | hyper];
+      4. its output splits into (scales, means) for the group's Gaussian likelihood."""
+    total = y.shape[1]
+    edges = [0, 6, 12, 24, 48, total]
+    rows = torch.arange(y.shape[2], device=y.device).view(-1, 1)
+    cols = torch.arange(y.shape[3], device=y.device).view(1, -1)
+    anchor = ((rows + cols) % 2 == 0)                    # [0::2, 0::2] and [1::2, 1::2]
+    result = {}
+    for g in range(5):
+        lo, hi = edges[g], edges[g + 1]
+        group = y[:, lo:hi]
+        visible = ste_round(group).masked_fill(anchor, 0.0)
+        ctx = context_prediction_models[g](visible).masked_fill(~anchor, 0.0)
+        pieces = [ctx]
+        if g > 0:
+            pieces.append(channel_context_models[g - 1](ste_round(y[:, :lo])))
+        pieces.append(hyper_params)
+        scales, means = entropy_parameters[g](torch.cat(pieces, dim=1)).chunk(2, 1)
+        result[f"y_{g}"] = gaussian_conditional(group, scales, means=means)[1]
     y_hat = ste_round(y)
     if inv_gain is not None:
-        y_hat = y_hat * inv_gain.unsqueeze(0).unsqueeze(2).unsqueeze(3)
-    return likelihoods_list, y_hat
+        y_hat = y_hat * inv_gain.view(1, -1, 1, 1)
+    return result, y_hat
 
 
 # ------------------------------------------------------------------------------------------------------------------

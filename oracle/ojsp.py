@@ -13,38 +13,29 @@ def PSNR(x, y):
     return 10 * torch.log10(1 / torch.mean((x - y) ** 2))
 
 
-def optimize_down_sampling_ratio(model, x, dpb):
-    downsampling_ratios = [1, 1.25, 1.5, 1.75, 2, 2.25, 2.5, 2.75, 3, 3.25, 3.5, 3.75, 4, 4.25, 4.5, 4.75, 5, 5.25,
-                           5.5, 5.75, 6, 6.25, 6.5, 6.75, 7, 7.25, 7.5, 7.75, 8, 8.25, 8.5, 8.75]
-    best_psnr = -float("inf")
-    best_est_mv_down = None
-    best_ratio = None
-    psnrs = []
-    for ratio in downsampling_ratios:
-        x_down = F.interpolate(x, scale_factor=1 / ratio, mode="bilinear", antialias=True)
-        ref_frame_down = F.interpolate(dpb["ref_frame"], scale_factor=1 / ratio, mode="bilinear", antialias=True)
-        p = 8
-        _, _, h, w = x_down.size()
-        pad_bottom = (p - h % p) % p
-        pad_right = (p - w % p) % p
-        x_down_padded = F.pad(x_down, (0, pad_right, 0, pad_bottom))
-        ref_frame_down_padded = F.pad(ref_frame_down, (0, pad_right, 0, pad_bottom))
-        est_mv_down_padded = model.optic_flow(x_down_padded, ref_frame_down_padded)
-        est_mv_down = est_mv_down_padded[:, :, :h, :w]
-        est_mv_down = F.interpolate(est_mv_down, size=(x.shape[2], x.shape[3]), mode="bilinear", antialias=True) * ratio
-        x_hat = warp_ac1(dpb["ref_frame"], est_mv_down)
-        psnr = PSNR(x, x_hat)
-        psnrs.append(psnr)
-        if ratio == dpb["ref_down_ratio"]:
-            prev_ratio_psnr = psnr
-            prev_ratio_mv = est_mv_down
-        if psnr > best_psnr:
-            best_psnr = psnr
-            best_est_mv_down = est_mv_down
-            best_ratio = ratio
-    bias = 0.1
-    if (best_psnr - prev_ratio_psnr) < bias:
-        if dpb["ref_down_ratio"] != best_ratio:
-            best_est_mv_down = prev_ratio_mv
-            best_ratio = dpb["ref_down_ratio"]
-    return best_est_mv_down, best_ratio, torch.stack(psnrs)
+def _candidate(model, x, ref, ratio, multiple=8):
+    """One candidate of the search: shrink both frames by `ratio` (antialiased bilinear), pad bottom / right to a
+    multiple of 8, estimate motion on the small pair, crop, enlarge the field back and scale the vectors by `ratio`."""
+    small = [F.interpolate(t, scale_factor=1 / ratio, mode="bilinear", antialias=True) for t in (x, ref)]
+    h, w = small[0].shape[-2:]
+    pad = (0, (multiple - w % multiple) % multiple, 0, (multiple - h % multiple) % multiple)
+    mv = model.optic_flow(F.pad(small[0], pad), F.pad(small[1], pad))[:, :, :h, :w]
+    return F.interpolate(mv, size=tuple(x.shape[-2:]), mode="bilinear", antialias=True) * ratio
+
+
+def optimize_down_sampling_ratio(model, x, dpb, bias=0.1):
+    """Returns (motion field, ratio, PSNR per candidate).  Candidates 1, 1.25, ..., 8.75; the first strictly best PSNR
+    wins; if it beats the previous frame's ratio (dpb["ref_down_ratio"]) by less than `bias` dB the previous ratio and
+    its field are kept instead."""
+    ratios = [1 + 0.25 * i for i in range(32)]
+    ref = dpb["ref_frame"]
+    fields = [_candidate(model, x, ref, r) for r in ratios]
+    scores = [PSNR(x, warp_ac1(ref, mv)) for mv in fields]
+    best = 0
+    for i in range(1, len(ratios)):
+        if scores[i] > scores[best]:
+            best = i
+    keep = ratios.index(dpb["ref_down_ratio"])          # the reference fails with an unbound name if it is not listed
+    if (scores[best] - scores[keep]) < bias and ratios[keep] != ratios[best]:
+        best = keep
+    return fields[best], ratios[best], torch.stack(scores)
