@@ -182,3 +182,12 @@ def test_icip_constants_equal_the_reference():
     starts = sorted(set(bounds))
     sizes = tuple(b - a for a, b in zip([0] + starts[:-1], starts))
     assert sizes + (None,) == icip.ELIC_GROUPS
+
+
+def test_elic_group_layout_is_validated_before_any_kernel_runs():
+    from b200vc import icip
+    for M in (40, 48):          # 6 + 6 + 12 + 24 = 48 leaves nothing (or less) for the last group
+        with pytest.raises(ValueError):
+            icip.elic_context_likelihoods(torch.zeros(1, M, 2, 2), None, None, None, None, None)
+    with pytest.raises(ValueError):
+        icip.elic_context_likelihoods(torch.zeros(1, 64, 2, 2), None, None, None, None, None, group_sizes=(6, 6))

@@ -138,6 +138,8 @@ def elic_context_likelihoods(y, hyper_params, context_prediction_models, channel
     sizes, start = [], 0
     for s in group_sizes:
         s = M - start if s is None else s
+        if s <= 0:
+            raise ValueError(f"channel groups {group_sizes} do not fit {M} channels")
         sizes.append((start, start + s))
         start += s
     if start != M:
