@@ -255,7 +255,9 @@ B200VC_API int b200vc_sse_u8_f32(const float* a, const float* b, double* partial
  *   symbols, indexes int32 [n_symbols]; cdf int32 [rows, cdf_stride]; cdf_len, offset int32 [rows].
  *   encode: scratch uint16 [n_streams, b200vc_rans_scratch_words(stream_len)], sizes_words int32 [n_streams] (out).
  *   compact: offsets_words int64 [n_streams] = exclusive prefix sum of sizes_words; out uint16 [sum(sizes)].
- *   decode: payload/offsets as produced by compact.
+ *   decode: payload / offsets_words / sizes_words as produced by encode + compact (they come from an untrusted
+ *           container: no stream reads past its own words); status int32 [1] (may be NULL), zeroed by the caller,
+ *           becomes 1 when a stream over-ran, stopped short or did not return to the initial coder state.
  */
 B200VC_API int b200vc_rans_scratch_words(int stream_len);
 B200VC_API int b200vc_rans_encode(const int32_t* symbols, const int32_t* indexes, const int32_t* cdf,
@@ -263,9 +265,10 @@ B200VC_API int b200vc_rans_encode(const int32_t* symbols, const int32_t* indexes
                                   int stream_len, uint16_t* scratch, int32_t* sizes_words, void* stream);
 B200VC_API int b200vc_rans_compact(const uint16_t* scratch, int stream_len, const int32_t* sizes_words,
                                    const int64_t* offsets_words, int n_streams, uint16_t* out, void* stream);
-B200VC_API int b200vc_rans_decode(const uint16_t* payload, const int64_t* offsets_words, const int32_t* indexes,
-                                  const int32_t* cdf, const int32_t* cdf_len, const int32_t* offset, int cdf_stride,
-                                  int64_t n_symbols, int stream_len, int32_t* symbols_out, void* stream);
+B200VC_API int b200vc_rans_decode(const uint16_t* payload, const int64_t* offsets_words, const int32_t* sizes_words,
+                                  const int32_t* indexes, const int32_t* cdf, const int32_t* cdf_len,
+                                  const int32_t* offset, int cdf_stride, int64_t n_symbols, int stream_len,
+                                  int32_t* symbols_out, int32_t* status, void* stream);
 
 #ifdef __cplusplus
 }

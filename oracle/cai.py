@@ -373,7 +373,10 @@ class MeanScaleHyperprior(ScaleHyperprior):
         scales_hat, means_hat = gaussian_params.chunk(2, 1)
         y_hat, y_likelihoods = self.gaussian_conditional(y, scales_hat, means=means_hat)
         x_hat = self.g_s(y_hat)
-        return {"x_hat": x_hat, "likelihoods": {"y": y_likelihoods, "z": z_likelihoods}}
+        out = {"x_hat": x_hat, "likelihoods": {"y": y_likelihoods, "z": z_likelihoods}}
+        if getattr(self, "keep_latents", False):  # test hook (not CompressAI): what the entropy coder would see
+            out["latents"] = {"y_hat": y_hat, "z_hat": z_hat, "scales_hat": scales_hat, "means_hat": means_hat}
+        return out
 
     def update(self, scale_table=None, force=False):
         if scale_table is None:

@@ -66,6 +66,31 @@ def test_empty_and_truncated_streams():
         coding.parse_container(b"xxxx" + data[4:])
 
 
+def test_container_header_is_validated_before_anything_reaches_the_gpu():
+    """An untrusted .bin: n / stream_len / S / sizes must be mutually consistent (the GPU decoder indexes with them)."""
+    import struct
+    rng = np.random.default_rng(4)
+    cdf, cdf_len, offset = _tables(rng)
+    data = o_rans.encode(np.zeros(40, np.int32), np.zeros(40, np.int32), cdf, cdf_len, offset, 16)   # 3 streams
+    n, sl, S = struct.unpack_from("<III", data, 4)
+    assert (n, sl, S) == (40, 16, 3)
+    hdr = lambda n, sl, S: data[:4] + struct.pack("<III", n, sl, S) + data[16:]
+    with pytest.raises(ValueError, match="header mismatch"):
+        coding.parse_container(hdr(40, 16, 2))        # S too small: the kernel would index offsets[] past its end
+    with pytest.raises(ValueError, match="header mismatch"):
+        coding.parse_container(hdr(400, 16, 3))       # more symbols than the streams can hold
+    with pytest.raises(ValueError, match="header mismatch"):
+        coding.parse_container(hdr(40, 0, 3))         # stream_len 0
+    with pytest.raises(ValueError, match="truncated"):
+        coding.parse_container(data[:20])
+    bad = bytearray(data)
+    struct.pack_into("<I", bad, 16, 1)                # a stream shorter than its two state words
+    with pytest.raises(ValueError, match="stream size"):
+        coding.parse_container(bytes(bad))
+    with pytest.raises(ValueError, match="b2r1"):
+        coding.parse_container(b"b2r1")
+
+
 def test_cost_tracks_the_model():
     """Coding i.i.d. symbols from a row's own pmf costs ~ its entropy (+ framing)."""
     rng = np.random.default_rng(7)

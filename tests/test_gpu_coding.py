@@ -50,6 +50,38 @@ def test_empty_input_and_bad_streams():
         coding.rans_decode(data, torch.zeros(3, dtype=torch.int32, device="cuda"), t)
 
 
+def test_corrupt_containers_raise_instead_of_faulting():
+    """a corrupt / truncated stream must surface as a Python error, never as an out-of-bounds device read
+    (which would poison the CUDA context).  Header lies are caught on the host; payload damage by the kernel's own
+    end-of-stream / final-state check."""
+    import struct
+    rng = np.random.default_rng(9)
+    cdf, cdf_len, offset = _random_tables(rng, 5, 40)
+    n = 3000
+    idx = rng.integers(0, 5, n).astype(np.int32)
+    sym = np.array([int(rng.integers(offset[r], offset[r] + cdf_len[r] - 2)) for r in idx], dtype=np.int32)
+    t = coding.Tables(cdf, cdf_len, offset, "cuda")
+    d_idx = torch.from_numpy(idx).cuda()
+    data = coding.rans_encode(torch.from_numpy(sym).cuda(), d_idx, t, stream_len=128)
+    S = struct.unpack_from("<I", data, 12)[0]
+    with pytest.raises(ValueError, match="header mismatch"):
+        coding.rans_decode(data[:12] + struct.pack("<I", S - 1) + data[16:], d_idx, t)
+    # move one word from stream 0 to stream 1: sizes still sum to the payload, both streams are now wrong
+    sizes = np.frombuffer(data, dtype="<u4", count=S, offset=16).copy()
+    sizes[0] -= 1
+    sizes[1] += 1
+    with pytest.raises(ValueError, match="corrupt stream"):
+        coding.rans_decode(data[:16] + sizes.astype("<u4").tobytes() + data[16 + 4 * S:], d_idx, t)
+    # flip payload bits in the middle of the container
+    bad = bytearray(data)
+    for k in range(len(bad) // 2, len(bad) // 2 + 64):
+        bad[k] ^= 0x5A
+    with pytest.raises(ValueError, match="corrupt stream"):
+        coding.rans_decode(bytes(bad), d_idx, t)
+    torch.cuda.synchronize()                                   # the context is still healthy
+    assert (coding.rans_decode(data, d_idx, t).cpu().numpy() == sym).all()
+
+
 def test_gaussian_tables_and_cost():
     """CDF rows follow GaussianConditional.update_scale_table; coding cost ~ the kernel's estimated bits."""
     from b200vc import modules, ops

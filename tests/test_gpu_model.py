@@ -52,7 +52,7 @@ def test_hyperprior_teacher_forced(models, which, ch):
     for k in ("y_symbols", "y_indexes", "z_symbols"):
         same = (so[k] == sp[k]).float().mean().item()
         print(f"{which} {k}: identical fraction {same:.6f}")
-        assert same > 0.999
+        assert same == 1.0  # north star: bit-matching symbols (measured 1.000000 on the default tcgen05 GDN path too)
     assert tuple(sp["shape"]) == tuple(so["shape"])
     bits_o = sum((-torch.log2(l.double())).sum().item() for l in ro["likelihoods"].values())
     bits_p = sum((-torch.log2(l.double())).sum().item() for l in rp["likelihoods"].values())
@@ -60,8 +60,8 @@ def test_hyperprior_teacher_forced(models, which, ch):
     assert abs(bits_p - bits_o) / bits_o < 1e-4
     assert abs((by + bz).sum().item() - bits_p) / bits_p < 1e-6  # bits-only pass == materialised likelihoods
     assert torch.equal(x_hat_b, rp["x_hat"])
-    close = ((rp["x_hat"] - ro["x_hat"]).abs() < 1e-3).float().mean().item()
-    assert close > 0.995, close
+    close = ((rp["x_hat"] - ro["x_hat"]).abs() < 1e-4).float().mean().item()
+    assert close > 0.9999, close
 
 
 def test_model_forward_matches_oracle(models, triple):
@@ -76,9 +76,9 @@ def test_model_forward_matches_oracle(models, triple):
     assert rel < 1e-4
     assert abs(rate_p.item() - rate_o.item()) / rate_o.item() < 1e-4
     assert isinstance(size_p, float) and rate_p.dtype == torch.float32
-    close = ((x_p - x_o).abs() < 1e-3).float().mean().item()
-    print(f"x_hat within 1e-3: {close:.5f}; max|diff| {(x_p - x_o).abs().max().item():.3e}")
-    assert close > 0.99
+    close = ((x_p - x_o).abs() < 1e-4).float().mean().item()
+    print(f"x_hat within 1e-4: {close:.5f}; max|diff| {(x_p - x_o).abs().max().item():.3e}")
+    assert close > 0.9999
     assert abs(bits.sum().item() - size_p) < 1e-6 * size_p
 
 
@@ -92,7 +92,9 @@ def test_model_forward_matches_reference_golden(models, triple):
     rel = abs(size_p - float(gold["synthetic_size64"])) / float(gold["synthetic_size64"])
     close = ((x_p - want).abs() < 2e-3).float().mean().item()
     print(f"vs reference golden: size rel {rel:.2e}, x_hat within 2e-3: {close:.5f}")
-    assert rel < 1e-3 and close > 0.98
+    # golden = CPU run of the reference's m.py (oneDNN convolutions), this = cuDNN: bits to the north-star bar,
+    # x_hat to the conv-backend noise amplified by the synthesis transform
+    assert rel < 1e-4 and close > 0.999
 
 
 def test_patch_swaps_kernels_into_a_foreign_model(models, triple):
@@ -125,7 +127,7 @@ def test_encode_b_symbols(models, triple):
         for k in ("y_symbols", "y_indexes", "z_symbols"):
             same = (a[k] == b[k]).float().mean().item()
             print(f"encode_B {nm} {k}: identical fraction {same:.6f}")
-            assert same > 0.995
+            assert same == 1.0
         assert a[k].dtype == torch.int32 and b[k].dtype == torch.int32
 
 

@@ -46,7 +46,7 @@ _SIGNATURES = {
     "b200vc_rans_scratch_words": (c_int, [c_int]),
     "b200vc_rans_encode": (c_int, [_fp, _fp, _fp, _fp, _fp, c_int, c_int64, c_int, _fp, _fp, c_void_p]),
     "b200vc_rans_compact": (c_int, [_fp, c_int, _fp, _fp, c_int, _fp, c_void_p]),
-    "b200vc_rans_decode": (c_int, [_fp, _fp, _fp, _fp, _fp, _fp, c_int, c_int64, c_int, _fp, c_void_p]),
+    "b200vc_rans_decode": (c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, c_int, c_int64, c_int, _fp, _fp, c_void_p]),
 }
 
 EXPORTS = tuple(_SIGNATURES)

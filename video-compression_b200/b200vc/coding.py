@@ -146,18 +146,34 @@ def rans_encode(symbols, indexes, tables, stream_len=STREAM_LEN):
 
 
 def parse_container(data):
-    if data[:4] != MAGIC:
+    """Header of an (untrusted) b2r1 container -> (n, stream_len, sizes[S], payload words).  Everything the GPU
+    decoder will index with is checked here: the stream count must be the one ``n`` and ``stream_len`` imply, every
+    stream holds at least its two state words and at most the encoder's worst case, and the payload length must
+    equal the sum of the stream sizes."""
+    if len(data) < 16 or data[:4] != MAGIC:
         raise ValueError("rans_decode: not a b2r1 stream")
     n, stream_len, S = struct.unpack_from("<III", data, 4)
+    if n == 0:
+        if S != 0 or len(data) != 16:
+            raise ValueError("rans_decode: malformed empty stream")
+        return 0, stream_len, np.zeros(0, dtype=np.int64), np.zeros(0, dtype="<u2")
+    if stream_len == 0 or S != (n + stream_len - 1) // stream_len:
+        raise ValueError(f"rans_decode: header mismatch ({n} symbols in streams of {stream_len} need "
+                         f"{(n + stream_len - 1) // max(stream_len, 1)} streams, header says {S})")
+    if len(data) < 16 + 4 * S or (len(data) - 16 - 4 * S) % 2:
+        raise ValueError("rans_decode: truncated header")
     sizes = np.frombuffer(data, dtype="<u4", count=S, offset=16).astype(np.int64)
     payload = np.frombuffer(data, dtype="<u2", offset=16 + 4 * S)
+    if sizes.min() < 2 or sizes.max() > 3 * stream_len + 2:
+        raise ValueError("rans_decode: a stream size is outside [2, 3 * stream_len + 2] words")
     if payload.size != int(sizes.sum()):
         raise ValueError("rans_decode: truncated payload")
     return n, stream_len, sizes, payload
 
 
 def rans_decode(data, indexes, tables):
-    """bytes + CDF-row indexes (flattened) -> int32 symbols on the indexes' device."""
+    """bytes + CDF-row indexes (flattened) -> int32 symbols on the indexes' device.  Raises ``ValueError`` for a
+    malformed or corrupt container (never an out-of-bounds device access)."""
     idx = indexes.reshape(-1).to(torch.int32).contiguous()
     n, stream_len, sizes, payload = parse_container(data)
     if idx.numel() != n:
@@ -168,12 +184,18 @@ def rans_decode(data, indexes, tables):
         raise RuntimeError("rans_decode: expected CUDA tensors (b200vc has no CPU fallback)")
     dev = idx.device
     offsets = torch.from_numpy(np.cumsum(sizes) - sizes).to(dev)
+    sizes32 = torch.from_numpy(sizes.astype(np.int32)).to(dev)
     words = torch.from_numpy(payload.astype(np.int16)).to(dev)
     out = torch.empty(n, dtype=torch.int32, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
     lib = _lib.load()
     ops._run("rans_decode", 8 * n, lambda: lib.b200vc_rans_decode(
-        words.data_ptr(), offsets.data_ptr(), idx.data_ptr(), tables.cdf.data_ptr(), tables.cdf_length.data_ptr(),
-        tables.offset.data_ptr(), tables.stride, n, stream_len, out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        words.data_ptr(), offsets.data_ptr(), sizes32.data_ptr(), idx.data_ptr(), tables.cdf.data_ptr(),
+        tables.cdf_length.data_ptr(), tables.offset.data_ptr(), tables.stride, n, stream_len, out.data_ptr(),
+        status.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    if status.item() != 0:
+        raise ValueError("rans_decode: corrupt stream (a stream over-ran, stopped short of its end or did not "
+                         "return to the coder's initial state)")
     return out
 
 

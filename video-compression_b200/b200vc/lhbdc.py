@@ -140,21 +140,30 @@ class Model(nn.Module):
         flow_ca = self.pad(F.avg_pool2d(self.FlowNet(x_current, x_after), 4))
         return torch.cat([flow_cb - flow_ab, flow_ca - flow_ba], dim=1), flow_ab, flow_ba, hh, ww
 
-    def forward_device(self, x_before, x_current, x_after):
+    def forward_device(self, x_before, x_current, x_after, return_parts=False):
         """The whole B-frame step with no host synchronisation (CUDA-graph capturable).
-        Returns (x_hat, bits[N] float64 = size_flow + size_residual, parts dict)."""
+        Returns (x_hat, bits[N] float64 = size_flow + size_residual, parts dict).  ``return_parts=True`` keeps every
+        intermediate of m.py:38-93 plus both compressors' symbols / CDF indexes in ``parts`` (the acceptance tests
+        compare them stage by stage with the reference path)."""
         diff, flow_ab, flow_ba, hh, ww = self.motion(x_before, x_current, x_after)
-        flow_hat, fb_y, fb_z = self.mv_compressor.forward_bits(diff)
+        mv = self.mv_compressor.forward_bits(diff, want_symbols=return_parts)
+        flow_hat, fb_y, fb_z = mv[:3]
         H, W = x_current.shape[-2:]
         if (hh * 4, ww * 4) != (H, W):
             raise RuntimeError(f"LHBDC needs H, W divisible by 4 (got {H}x{W})")
         warped = ops.warp2_lhbdc(x_before, x_after, flow_hat, flow_ab, flow_ba)  # [N,6,H,W] = cat(fw, bw)
         mask = self.masknet(warped)
         pred, residual, _ = ops.blend_residual("mask", mask, warped[:, 0:3], warped[:, 3:6], x_current)
-        res_hat, rb_y, rb_z = self.residual_compressor.forward_bits(residual)
+        rs = self.residual_compressor.forward_bits(residual, want_symbols=return_parts)
+        res_hat, rb_y, rb_z = rs[:3]
         x_hat = res_hat + pred
         bits_flow, bits_res = fb_y + fb_z, rb_y + rb_z
-        return x_hat, bits_flow + bits_res, {"bits_flow": bits_flow, "bits_residual": bits_res}
+        parts = {"bits_flow": bits_flow, "bits_residual": bits_res}
+        if return_parts:
+            parts.update(diff_flow=diff, flow_ab=flow_ab, flow_ba=flow_ba, flow_hat=flow_hat, warped=warped, mask=mask,
+                         pred=pred, residual=residual, res_hat=res_hat, mv=mv[3], res=rs[3],
+                         bits_flow_y=fb_y, bits_flow_z=fb_z, bits_res_y=rb_y, bits_res_z=rb_z)
+        return x_hat, bits_flow + bits_res, parts
 
     def forward(self, x_before, x_current, x_after, train):
         """m.py:32-98.  ``rate`` keeps the reference's definition ((rate_flow + rate_residual)/2 over the padded

@@ -355,17 +355,25 @@ def hyperprior_forward(mod, x):
     return {"x_hat": mod.g_s(y_hat), "likelihoods": {"y": y_lik, "z": z_lik}}
 
 
-def hyperprior_forward_bits(mod, x):
+def hyperprior_forward_bits(mod, x, want_symbols=False):
     """Same computation, but the likelihood tensors are never written to HBM: the quantise->CDF-difference->
-    -log2 pass reduces straight to per-sample bit totals.  Returns (x_hat, bits_y[N], bits_z[N]) (float64)."""
+    -log2 pass reduces straight to per-sample bit totals.  Returns (x_hat, bits_y[N], bits_z[N]) (float64).
+    ``want_symbols=True`` (the encoder's view of the same pass: LHBDC/model/layers.py:93-104) additionally returns a
+    dict with the int32 y symbols + CDF indexes, the z symbols and the latents they were taken from."""
     eb, gc = mod.entropy_bottleneck, mod.gaussian_conditional
     y = mod.g_a(x)
     z = mod.h_a(y)
-    rz = ops.entropy_bottleneck(z, eb_packed(eb), lik_bound=_lik_bound(eb), want_lik=False)
+    rz = ops.entropy_bottleneck(z, eb_packed(eb), lik_bound=_lik_bound(eb), want_lik=False, want_symbols=want_symbols)
     scales_hat, means_hat = mod.h_s(rz["z_hat"]).chunk(2, 1)
     ry = ops.gauss_cond(y, scales_hat, means_hat, scale_bound=_scale_bound(gc), lik_bound=_lik_bound(gc),
-                        want_lik=False)
-    return mod.g_s(ry["y_hat"]), ry["bits"], rz["bits"]
+                        want_lik=False, want_symbols=want_symbols,
+                        scale_table=gc.scale_table if want_symbols else None)
+    x_hat = mod.g_s(ry["y_hat"])
+    if want_symbols:
+        return x_hat, ry["bits"], rz["bits"], {
+            "y_symbols": ry["symbols"], "y_indexes": ry["indexes"], "z_symbols": rz["symbols"], "shape": z.size()[-2:],
+            "y": y, "z": z, "scales_hat": scales_hat, "means_hat": means_hat, "y_hat": ry["y_hat"], "z_hat": rz["z_hat"]}
+    return x_hat, ry["bits"], rz["bits"]
 
 
 def hyperprior_symbols(mod, x):

@@ -81,20 +81,31 @@ __global__ void rans_compact_kernel(const uint16_t* __restrict__ scratch, int sc
   for (int k = lane; k < n; k += 32) dst[k] = src[k];
 }
 
+// A stream never reads past its own words: a truncated / corrupt container yields zeros instead of an
+// out-of-bounds access, and is reported through `status` (a well-formed stream ends exactly at its last word with
+// the state back at the encoder's initial value).
 __global__ void __launch_bounds__(128)
 rans_decode_kernel(const uint16_t* __restrict__ payload, const int64_t* __restrict__ offsets,
-                   const int32_t* __restrict__ indexes, RansTables t, int64_t n_symbols, int stream_len,
-                   int32_t* __restrict__ symbols, int n_streams) {
+                   const int32_t* __restrict__ sizes, const int32_t* __restrict__ indexes, RansTables t,
+                   int64_t n_symbols, int stream_len, int32_t* __restrict__ symbols, int n_streams,
+                   int32_t* __restrict__ status) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_streams) return;
   const int64_t lo = (int64_t)s * stream_len;
   const int64_t hi = lo + stream_len < n_symbols ? lo + stream_len : n_symbols;
   const uint16_t* p = payload + offsets[s];
-  uint32_t x = ((uint32_t)p[0] << 16) | p[1];
-  p += 2;
+  const uint16_t* const end = p + sizes[s];
+  bool overrun = false;
+  auto next = [&]() -> uint32_t {
+    if (p < end) return *p++;
+    overrun = true;
+    return 0u;
+  };
+  uint32_t x = next() << 16;
+  x |= next();
   auto advance = [&](uint32_t start, uint32_t freq) {
     x = freq * (x >> 16) + (x & 0xFFFFu) - start;
-    if (x < kRansL) x = (x << 16) | *p++;
+    if (x < kRansL) x = (x << 16) | next();
   };
   for (int64_t i = lo; i < hi; ++i) {
     const int row = __ldg(indexes + i);
@@ -120,6 +131,7 @@ rans_decode_kernel(const uint16_t* __restrict__ payload, const int64_t* __restri
     }
     symbols[i] = value + __ldg(t.offset + row);
   }
+  if (status != nullptr && (overrun || p != end || x != kRansL)) atomicOr(status, 1);
 }
 
 }  // namespace b200vc
@@ -155,16 +167,17 @@ extern "C" int b200vc_rans_compact(const uint16_t* scratch, int stream_len, cons
   return check_launch("rans_compact");
 }
 
-extern "C" int b200vc_rans_decode(const uint16_t* payload, const int64_t* offsets_words, const int32_t* indexes,
-                                  const int32_t* cdf, const int32_t* cdf_len, const int32_t* offset, int cdf_stride,
-                                  int64_t n_symbols, int stream_len, int32_t* symbols_out, void* stream) {
-  B200VC_REQUIRE(payload && offsets_words && indexes && cdf && cdf_len && offset && symbols_out,
+extern "C" int b200vc_rans_decode(const uint16_t* payload, const int64_t* offsets_words, const int32_t* sizes_words,
+                                  const int32_t* indexes, const int32_t* cdf, const int32_t* cdf_len,
+                                  const int32_t* offset, int cdf_stride, int64_t n_symbols, int stream_len,
+                                  int32_t* symbols_out, int32_t* status, void* stream) {
+  B200VC_REQUIRE(payload && offsets_words && sizes_words && indexes && cdf && cdf_len && offset && symbols_out,
                  "rans_decode: null pointer");
   B200VC_REQUIRE(n_symbols > 0 && stream_len > 0 && cdf_stride > 2, "rans_decode: bad size");
   const int64_t n_streams = (n_symbols + stream_len - 1) / stream_len;
   B200VC_REQUIRE(n_streams < (1ll << 31), "rans_decode: too many streams");
   RansTables t{cdf, cdf_len, offset, cdf_stride};
   rans_decode_kernel<<<(unsigned)((n_streams + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-      payload, offsets_words, indexes, t, n_symbols, stream_len, symbols_out, (int)n_streams);
+      payload, offsets_words, sizes_words, indexes, t, n_symbols, stream_len, symbols_out, (int)n_streams, status);
   return check_launch("rans_decode");
 }
