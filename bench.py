@@ -1,17 +1,25 @@
 #!/usr/bin/env python
-"""bench.py -- BASELINE.json metric: 1080p B-frames/s (encode+decode) of the LHBDC hierarchical GOP-8 codec,
-plus hot-path HBM GB/s vs peak.
+"""bench.py -- BASELINE.json metric: 1080p B-frames/s (encode+decode) of the hierarchical B-frame codecs, plus
+hot-path HBM GB/s vs peak, for every configuration BASELINE.json names.
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's arm (b200vc kernels)
-    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle), rank 0 only
+    python bench.py --gpus N --steps K --warmup W                       # configs[1], this repo's arm (default)
+    python bench.py --impl reference --gpus N --steps K --warmup W      # the reference's CPU path (oracle), rank 0
+    python bench.py --workload {lhbdc_gop8, flex_gop16_allq, icip_gop16, ojsp_search_4k, lhbdc_frames} ...
+    python bench.py --sequence-frames 601 ...                           # strong scaling: ONE shared sequence, GOP-sharded
 
-A "step" = one GOP-8 of synthetic 1920x1080 video per GPU (7 B-frames; frames of one hierarchy level are one
-batched Model call; anchors uncoded).  One encode+decode = one ``Model.forward(train=False)`` per B-frame
-(SURVEY.md 8d).  N > 1 is launched by torchrun, one rank per GPU; GOPs are independent, so ranks share no
-data-path collective (weak scaling) -- only the timing max and the per-frame records cross ranks.
+workload          BASELINE.json config                                   step (per rank)
+lhbdc_gop8        [1] LHBDC GOP-8, synthetic 1920x1080                   --gops-per-step GOP-8s (7 B-frames each)
+lhbdc_frames      [0] LHBDC encode_B/decode_B on the bundled frames      one B-frame through real rANS bitstreams
+flex_gop16_allq   [2] Flex-Rate GOP-16, all 8 `qualities` rows           this rank's share of 8 x GOP-16 (strong)
+icip_gop16        [3] ICIP2024 FlowGuidedB, GOP-16 + down-ratio search   one GOP-16 per level s (5 levels)
+ojsp_search_4k    [4] OJSP2025 32-ratio warp+PSNR search at 3840x2160    one P-frame's search
 
-One JSON line on stdout (rank 0).  ``value``: inputs resident in HBM; ``e2e``: same steps through the public
-API from pinned host frames, H2D + D2H inside the timed region.
+One encode+decode = one ``Model.forward(train=False)`` per B-frame.  N > 1 is launched by torchrun, one
+rank per GPU; GOPs are independent, so ranks share no data-path collective -- only the timing max and the per-frame
+records cross ranks.
+
+One JSON line on stdout (rank 0).  ``value``: inputs resident in HBM; ``e2e``: the same steps through the public API
+from pinned host frames, H2D of the frames and D2H of the decoded frames + bits inside the timed region.
 """
 import argparse
 import json
@@ -27,11 +35,10 @@ for p in (ROOT, os.path.join(ROOT, "video-compression_b200")):
         sys.path.insert(0, p)
 
 import torch  # noqa: E402
+import torch.nn as nn  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
 
-METRIC = "1080p B-frames/s encode+decode (LHBDC hierarchical GOP-8)"
-UNIT = "B-frames/s"
-HOT_KERNELS = ("gdn_f32", "warp_f32", "warp2_lhbdc_f32", "blend_residual_f32", "gauss_cond_f32",
-               "entropy_bottleneck_f32", "spynet_level_f32", "spynet_pyramid_f32")
+WORKLOADS = ("lhbdc_gop8", "lhbdc_frames", "flex_gop16_allq", "icip_gop16", "ojsp_search_4k")
 
 
 def parse():
@@ -40,16 +47,27 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200vc", choices=["b200vc", "reference"])
-    ap.add_argument("--height", type=int, default=1080)
-    ap.add_argument("--width", type=int, default=1920)
-    ap.add_argument("--gops-per-step", type=int, default=1)
+    ap.add_argument("--workload", default="lhbdc_gop8", choices=WORKLOADS)
+    ap.add_argument("--height", type=int, default=None)
+    ap.add_argument("--width", type=int, default=None)
+    ap.add_argument("--gops-per-step", type=int, default=1,
+                    help="GOPs coded as one batch (frames of one hierarchy level of all of them = one Model call)")
+    ap.add_argument("--sequence-frames", type=int, default=0,
+                    help="lhbdc_gop8 strong scaling: one shared seeded sequence of this many frames, GOP-sharded over "
+                         "the ranks (SURVEY 8e); a step = the whole sequence")
     ap.add_argument("--conv-tf32", action="store_true",
                     help="let cuDNN use TF32 for the (out-of-scope) convolutions, as torch defaults do")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end timed region (profiling runs)")
     ap.add_argument("--ncu-range", action="store_true",
                     help="bracket the timed region with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     ap.add_argument("--cpu-budget-s", type=float, default=240.0, help="wall-clock budget of the reference arm")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.height is None:
+        a.height = 2160 if a.workload == "ojsp_search_4k" else 1080
+    if a.width is None:
+        a.width = 3840 if a.workload == "ojsp_search_4k" else 1920
+    return a
 
 
 # ------------------------------------------------------------------------------------------ helpers
@@ -114,7 +132,90 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def build_product_model(device):
+def _threads():
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    return cores
+
+
+def _median(xs):
+    return sorted(xs)[len(xs) // 2]
+
+
+def _timed_cpu(fn, steps, warmup, budget_s, first=None):
+    """Run ``fn`` warmup + steps times (at least once) inside ``budget_s``; returns the list of timed durations."""
+    times, done, t_start = [], 0, time.perf_counter()
+    if first is not None:
+        done = 1
+        if warmup == 0:
+            times.append(first)
+    while done < warmup + steps or not times:
+        t0 = time.perf_counter()
+        fn()
+        dt = time.perf_counter() - t0
+        if done >= warmup:
+            times.append(dt)
+        done += 1
+        if times and time.perf_counter() - t_start + dt > budget_s:
+            break
+    return times
+
+
+def pin(t):
+    return t.pin_memory() if torch.cuda.is_available() else t
+
+
+# ============================================================================================ workloads
+class Workload:
+    """One BASELINE.json configuration: synthetic inputs, the product step (resident / end-to-end), the reference's
+    CPU path on a bounded sample, and the parity check between the two."""
+    name = ""
+    metric = "1080p B-frames/s encode+decode"
+    unit = "B-frames/s"
+    scaling = "weak"
+    hot_kernels = ()
+
+    def __init__(self, args):
+        self.args = args
+        self.h, self.w = args.height, args.width
+
+    # -- product arm
+    def setup(self, device, rank, world):
+        raise NotImplementedError
+
+    def step(self, i, e2e):
+        raise NotImplementedError
+
+    def units_per_step(self):          # units (frames) this rank codes per step
+        raise NotImplementedError
+
+    def total_units_per_step(self, world):
+        return self.units_per_step() * world
+
+    def records(self, rank):           # [n, 4] float64 (unit, frame, bits, sse) of the last step, or None
+        return None
+
+    h2d_bytes = 0
+    d2h_bytes = 0
+
+    def config(self, world):
+        return {}
+
+    # -- reference arm / cpu baseline: returns dict(value, cores, sample, ms, extra)
+    def cpu_sample(self, steps, warmup, budget_s):
+        raise NotImplementedError
+
+    def parity(self, cpu_extra):
+        return None
+
+
+def _conv_math(args):
+    return ("cuDNN TF32 allowed (torch default, as the reference runs)" if args.conv_tf32
+            else "cuDNN fp32 (allow_tf32=False): the configuration parity is proven in")
+
+
+# ------------------------------------------------------------------------------------ LHBDC GOP-8 (configs[1])
+def build_lhbdc(device):
     import b200vc
     from b200vc import synthetic
     torch.manual_seed(0)
@@ -125,7 +226,7 @@ def build_product_model(device):
     return model.to(device)
 
 
-def build_oracle_model():
+def build_lhbdc_oracle():
     """Same weights as the product arm (state dict copied), torch ops only, CPU."""
     import b200vc
     from b200vc import synthetic
@@ -137,52 +238,644 @@ def build_oracle_model():
     orc.load_state_dict(prod.state_dict())
     orc.mv_compressor.update(force=True)
     orc.residual_compressor.update(force=True)
+    for c in (orc.mv_compressor, orc.residual_compressor):
+        c.keep_latents = True
     return orc
 
 
-def cpu_reference_frames_per_s(args, steps, warmup, budget_s):
-    """The reference's CPU PyTorch path (oracle restatement: compressai is not installable offline), all host
-    threads, on a bounded sample: the level-0 B-frame of a GOP-8 (anchors 0 and 8).  If the full frame would
-    blow the time budget the sample shrinks to a top band of the frame and is scaled by its pixel share."""
-    from b200vc import synthetic
-    from b200vc.lhbdc import reflect_pad64
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    orc = build_oracle_model()
-    frames = reflect_pad64(synthetic.make_sequence(9, args.height, args.width, seed=1234))
-    full_rows = frames.shape[2]
-    n_total = steps + warmup
+def _oracle_symbols(result):
+    """int32 symbols of both latents from an oracle hyperprior result kept with ``keep_latents``."""
+    lat = result["latents"]
+    return torch.round(lat["y_hat"] - lat["means_hat"]).int()
 
-    def one(rows):
-        t0 = time.perf_counter()
+
+class LhbdcGop8(Workload):
+    name = "lhbdc_gop8"
+    metric = "1080p B-frames/s encode+decode (LHBDC hierarchical GOP-8)"
+    hot_kernels = ("gdn_f32", "warp_f32", "warp2_lhbdc_f32", "blend_residual_f32", "gauss_cond_f32",
+                   "entropy_bottleneck_f32", "spynet_level_f32", "spynet_pyramid_f32", "sse_u8_f32")
+
+    def __init__(self, args):
+        super().__init__(args)
+        from b200vc import gop
+        self.G = max(1, args.gops_per_step)
+        self.T = int(args.sequence_frames)
+        self.scaling = "strong" if self.T else "weak"
+        self.sched = gop.LHBDC_GOP8
+        self.n_units = gop.num_gops(self.T, self.sched.gop) if self.T else 0
+
+    def setup(self, device, rank, world):
+        from b200vc import gop, synthetic
+        from b200vc.lhbdc import reflect_pad64
+        self.device, self.rank, self.world = device, rank, world
+        self.sched = gop.LHBDC_GOP8
+        self.model = build_lhbdc(device)
+        self.coder = gop.GopCoder(self.model, self.sched)
+        g, h, w, G = self.sched.gop, self.h, self.w, self.G
+        if self.T:
+            # one shared sequence; this rank holds the frames of its contiguous block of GOPs (anchors duplicated
+            # at shard boundaries: SURVEY 8e)
+            mine = gop.shard_units(self.n_units, world, rank)
+            self.my_units = list(mine)
+            lo, hi = (mine.start, mine.stop) if len(mine) else (0, 0)
+            host = synthetic.make_frames(range(lo * g, hi * g + 1) if len(mine) else [], h, w, seed=1234)
+            self.host = pin(host)
+            self.unit_lo = lo
+            self.dev = reflect_pad64(self.host.to(device)) if len(mine) else None
+            self.batches = [self.my_units[k:k + G] for k in range(0, len(self.my_units), G)]
+            cap = max((len(b) for b in self.batches), default=1)
+        else:
+            # two distinct GOP batches per rank, alternated across steps; one batch = G*9 frames = G*224 MB > L2
+            self.n_sets = 2
+            host = synthetic.make_sequence(self.n_sets * G * g + 1, h, w, seed=1234 + rank)
+            idx = [[k * g + t for t in range(g + 1)] for k in range(self.n_sets * G)]
+            self.host_sets = [pin(torch.stack([host[idx[s * G + k]] for k in range(G)], 0)) for s in range(self.n_sets)]
+            self.dev_sets = [reflect_pad64(hs.to(device).flatten(0, 1)).unflatten(0, (G, g + 1)) for hs in self.host_sets]
+            self.my_units = [rank * G + k for k in range(G)]
+            cap = G
+        nb = len(self.sched.refs)
+        self.out_host = pin(torch.empty((cap, nb, 3, h, w)))       # decoded B-frames land here (e2e)
+        self.b_idx = torch.tensor(sorted(self.sched.refs), device=device)
+        self.h2d_bytes = (self.host.numel() if self.T else self.host_sets[0].numel()) * 4
+        self.d2h_bytes = (len(self.my_units) if self.T else G) * nb * (3 * h * w * 4 + 16)
+        self._last = None
+
+    def units_per_step(self):
+        return len(self.my_units) * len(self.sched.refs)
+
+    def total_units_per_step(self, world):
+        from b200vc import gop
+        if self.T:
+            return gop.num_gops(self.T, self.sched.gop) * len(self.sched.refs)
+        return self.units_per_step() * world
+
+    def _gops(self, frames_dev, units):
+        g = self.sched.gop
+        return torch.stack([frames_dev[(u - self.unit_lo) * g:(u - self.unit_lo) * g + g + 1] for u in units], 0)
+
+    def _code(self, x, e2e):
+        h, w = self.h, self.w
+        if not e2e:
+            bits, sse = self.coder.code(x, (h, w))
+            return bits, sse
+        bits, sse, dec = self.coder.code(x, (h, w), want_decoded=True)
+        n = x.shape[0]
+        self.out_host[:n].copy_(dec.index_select(1, self.b_idx)[..., :h, :w], non_blocking=True)   # D2H: decoded frames
+        return bits, sse
+
+    def step(self, i, e2e):
+        from b200vc.lhbdc import reflect_pad64
+        g = self.sched.gop
+        if self.T:
+            frames = reflect_pad64(self.host.to(self.device, non_blocking=True)) if e2e else self.dev   # H2D (pinned)
+            outs = [self._code(self._gops(frames, b), e2e) for b in self.batches]
+            bits = torch.cat([o[0] for o in outs], 0) if outs else torch.zeros((0, g + 1), dtype=torch.float64)
+            sse = torch.cat([o[1] for o in outs], 0) if outs else torch.zeros((0, g + 1), dtype=torch.float64)
+        else:
+            if e2e:
+                x = self.host_sets[i % self.n_sets].to(self.device, non_blocking=True)                  # H2D (pinned)
+                x = reflect_pad64(x.flatten(0, 1)).unflatten(0, (self.G, g + 1))
+            else:
+                x = self.dev_sets[i % self.n_sets]
+            bits, sse = self._code(x, e2e)
+        self._last = (bits, sse)
+        if e2e:
+            return torch.stack([bits, sse]).to("cpu")      # D2H of the per-frame bits / SSE (synchronises the step)
+        return None
+
+    def records(self, rank):
+        bits, sse = self._last
+        bits_c, sse_c = bits.cpu(), sse.cpu()
+        rec = []
+        for k, u in enumerate(self.my_units):
+            for f in self.sched.order:
+                rec.append([float(u), float(f), bits_c[k, f].item(), sse_c[k, f].item()])
+        return torch.tensor(rec, dtype=torch.float64).reshape(-1, 4)
+
+    def config(self, world):
+        h, w = self.h, self.w
+        c = {
+            "workload": f"LHBDC hierarchical GOP-8 B-frame encode/decode, synthetic {w}x{h}, 1 B200 per rank "
+                        "(BASELINE.json configs[1])",
+            "step": (f"one shared {self.T}-frame sequence = {self.n_units} GOP-8, contiguous blocks "
+                     f"of GOPs per rank, {self.G} GOPs per batch" if self.T else
+                     f"{self.G} GOP-8 per GPU = {self.G * len(self.sched.refs)} B-frames, levels batched "
+                     f"({self.G}/{2 * self.G}/{4 * self.G} frames per call)"),
+            "weights": "random-init (seed 0) + deterministic calibration (b200vc/synthetic.py)",
+            "anchors": "uncoded source frames (I-frame codec is outside the B-frame hot path)",
+            "conv_math": _conv_math(self.args),
+            "l2": "inputs larger than L2: each step streams >= 224 MB of frames + GBs of activations; "
+                  "two GOP sets alternate",
+            "parallelism": f"gop-sharded x{world}",
+        }
+        if self.T:
+            from b200vc import gop
+            per = [len(gop.shard_units(self.n_units, world, r)) for r in range(world)]
+            c["units_per_rank"] = per
+            c["efficiency_expected"] = self.n_units / (world * max(per)) if max(per) else None
+        return c
+
+    # ---- reference arm
+    def cpu_sample(self, steps, warmup, budget_s):
+        """The reference's CPU PyTorch path (oracle restatement: compressai is not installable offline), all host
+        threads, on a bounded sample: the level-0 B-frame of the first GOP-8 (anchors 0 and 8).  If the full frame
+        would blow the budget the sample shrinks to a top band of the frame and is scaled by its pixel share."""
+        from b200vc import synthetic
+        from b200vc.lhbdc import reflect_pad64
+        cores = _threads()
+        orc = build_lhbdc_oracle()
+        frames = reflect_pad64(synthetic.make_frames(range(9), self.h, self.w, seed=1234) if self.T else
+                               synthetic.make_sequence(9, self.h, self.w, seed=1234))
+        full_rows = frames.shape[2]
+        keep = {}
+
+        def one(rows):
+            t0 = time.perf_counter()
+            with torch.no_grad():
+                x_hat, _, size, parts = orc(frames[0:1, :, :rows], frames[4:5, :, :rows], frames[8:9, :, :rows],
+                                            train=False, return_parts=True)
+            dt = time.perf_counter() - t0
+            keep.update(rows=rows, size64=parts["size64"], x_hat=x_hat,
+                        mv_y=_oracle_symbols(parts["flow_result"]), res_y=_oracle_symbols(parts["residual_result"]))
+            return dt
+
+        rows = full_rows
+        first = one(rows)
+        if first * (steps + warmup) > budget_s:
+            for cand in (full_rows // 2, full_rows // 4, full_rows // 8):
+                cand -= cand % 64
+                if cand >= 192:
+                    rows = cand
+                    if first * (cand / full_rows) * (steps + warmup) <= budget_s:
+                        break
+            times = _timed_cpu(lambda: one(rows), steps, min(warmup, 1), budget_s)
+        else:
+            times = _timed_cpu(lambda: one(rows), steps, warmup, budget_s, first=first)
+        share = rows / full_rows
+        med = _median(times)
+        sample = (f"level-0 B-frame of a GOP-8, {rows}x{frames.shape[3]} of the padded {full_rows}x{frames.shape[3]} frame"
+                  f"{'' if rows == full_rows else f' (scaled by pixel share {share:.3f})'}; median of {len(times)} runs; "
+                  f"oracle torch path, fp32")
+        return {"value": share / med, "cores": cores, "sample": sample, "ms": med * 1e3, "extra": keep}
+
+    def parity(self, cpu):
+        """GPU arm vs the CPU reference path on the SAME frame (frames 0, 4, 8 of the seed-1234 sequence): free-running,
+        i.e. cuDNN vs oneDNN convolutions upstream of every quantiser (the same-device, stage-wise comparison with
+        the bit-exact bars is tests/test_gpu_acceptance.py)."""
+        from b200vc import synthetic
+        from b200vc.lhbdc import reflect_pad64
+        rows = cpu["rows"]
+        frames = reflect_pad64((synthetic.make_frames(range(9), self.h, self.w, seed=1234) if self.T else
+                                synthetic.make_sequence(9, self.h, self.w, seed=1234)).to(self.device))
         with torch.no_grad():
-            orc(frames[0:1, :, :rows], frames[4:5, :, :rows], frames[8:9, :, :rows], train=False)
-        return time.perf_counter() - t0
+            x_hat, bits, p = self.model.forward_device(frames[0:1, :, :rows], frames[4:5, :, :rows], frames[8:9, :, :rows],
+                                                       return_parts=True)
+        eq = [(p["mv"]["y_symbols"].cpu() == cpu["mv_y"]).float().mean().item(),
+              (p["res"]["y_symbols"].cpu() == cpu["res_y"]).float().mean().item()]
+        n = [cpu["mv_y"].numel(), cpu["res_y"].numel()]
+        dx = (x_hat.cpu() - cpu["x_hat"]).abs()
+        return {"frame": "GOP 0, frame 4 (refs 0 and 8)", "rows": rows,
+                "bits_gpu": bits.item(), "bits_cpu_oracle": cpu["size64"],
+                "bits_rel": abs(bits.item() - cpu["size64"]) / cpu["size64"],
+                "symbols_equal_frac": (eq[0] * n[0] + eq[1] * n[1]) / (n[0] + n[1]),
+                "symbols_equal_frac_mv_y": eq[0], "symbols_equal_frac_res_y": eq[1],
+                "x_hat_max_abs_diff": dx.max().item(), "x_hat_frac_within_1e-3": (dx < 1e-3).float().mean().item(),
+                "note": "free-running GPU (cuDNN) vs CPU (oneDNN) run of the same fp32 graph; symbol differences "
+                        "are convolution-backend rounding upstream of the quantisers"}
 
-    rows = full_rows
-    first = one(rows)
-    times = [] if warmup > 0 else [first]
-    done = 1
-    if first * n_total > budget_s:
-        for cand in (full_rows // 2, full_rows // 4, full_rows // 8):
-            cand -= cand % 64
-            if cand >= 192:
-                rows = cand
-                if first * (cand / full_rows) * n_total <= budget_s:
-                    break
-        times, done = [], min(done, warmup)  # the full-size run only counts as a warm-up
-    while done < n_total or not times:
-        dt = one(rows)
-        if done >= warmup:
-            times.append(dt)
-        done += 1
-    share = rows / full_rows
-    med = sorted(times)[len(times) // 2]
-    value = share / med
-    sample = (f"level-0 B-frame of a GOP-8, {rows}x{frames.shape[3]} of the padded {full_rows}x{frames.shape[3]} frame"
-              f"{'' if rows == full_rows else f' (scaled by pixel share {share:.3f})'}; median of {len(times)} runs; "
-              f"oracle torch path, fp32")
-    return value, cores, sample, sum(times) / max(1, len(times)) * 1e3
+
+# -------------------------------------------------------------------- LHBDC bundled frames (configs[0])
+class LhbdcFrames(Workload):
+    name = "lhbdc_frames"
+    metric = "1080p B-frames/s encode+decode (LHBDC encode_B + decode_B on the bundled frames, real bitstreams)"
+    hot_kernels = LhbdcGop8.hot_kernels + ("rans_encode", "rans_decode", "rans_compact")
+
+    def _frames(self):
+        import numpy as np
+        from b200vc.lhbdc import reflect_pad64
+        z = np.load(os.path.join(ROOT, "tests", "golden", "lhbdc_frames_1080p.npz"))
+        f = torch.from_numpy(z["frames_u8"]).float() / 255.0          # (ref_1, current, ref_2)
+        return f
+
+    def setup(self, device, rank, world):
+        self.device = device
+        self.model = build_lhbdc(device)
+        self.host = pin(self._frames())
+        from b200vc.lhbdc import reflect_pad64
+        self.dev = reflect_pad64(self.host.to(device))
+        self.h, self.w = self.host.shape[-2:]
+        self.out_host = pin(torch.empty((1, 3, self.h, self.w)))
+        self.h2d_bytes = self.host.numel() * 4
+        self.d2h_bytes = 3 * self.h * self.w * 4
+        self._last = None
+
+    def units_per_step(self):
+        return 1
+
+    def step(self, i, e2e):
+        import b200vc
+        from b200vc import ops
+        from b200vc.lhbdc import reflect_pad64
+        with torch.no_grad():
+            f = reflect_pad64(self.host.to(self.device, non_blocking=True)) if e2e else self.dev
+            xb, xc, xa = f[0:1], f[1:2], f[2:3]
+            mv, res = b200vc.encode_B(self.model, xa, xc, xb)                      # LHBDC/encode_B.py:71-105
+            dec = b200vc.decode_B(xb, xa, self.model, mv["strings"], res["strings"], mv["shape"], res["shape"])
+            nbytes = sum(len(s[0]) for s in mv["strings"]) + sum(len(s[0]) for s in res["strings"])
+            sse = ops.sse_u8(dec, xc, self.h, self.w)
+            if e2e:
+                self.out_host.copy_(dec[..., :self.h, :self.w], non_blocking=True)
+                sse = sse.cpu()
+            self._last = (8.0 * nbytes, sse)
+        return None
+
+    def records(self, rank):
+        bits, sse = self._last
+        return torch.tensor([[float(rank), 1.0, bits, float(sse.cpu()[0])]], dtype=torch.float64)
+
+    def config(self, world):
+        return {"workload": "LHBDC encode_B.py / decode_B.py B-frame coding of the bundled LHBDC/frames test triple "
+                            "(ref_1, current, ref_2; 1920x1080), real rANS bitstreams (BASELINE.json configs[0])",
+                "step": "one B-frame: encode_B (two compressors -> 4 byte strings) + decode_B",
+                "weights": "random-init (seed 0) + deterministic calibration (no checkpoints offline)",
+                "conv_math": _conv_math(self.args),
+                "l2": "75 MB of frames + GBs of activations per step (inputs larger than L2 through the conv stacks)",
+                "parallelism": f"replicas x{world}"}
+
+    def cpu_sample(self, steps, warmup, budget_s):
+        """The body of the reference's encode_B (LHBDC/encode_B.py:71-105) with rANS replaced by symbols + indexes (no
+        CPU coder offline: SURVEY 8d config 1) plus Model.forward for the reconstruction, oracle torch path on all host
+        threads."""
+        from b200vc.lhbdc import reflect_pad64
+        from oracle import lhbdc as o_lhbdc
+        cores = _threads()
+        orc = build_lhbdc_oracle()
+        f = reflect_pad64(self._frames())
+        xb, xc, xa = f[0:1], f[1:2], f[2:3]
+        keep = {}
+
+        def one():
+            with torch.no_grad():
+                mv, res = o_lhbdc.encode_B_symbols(orc, xa, xc, xb)
+            keep.update(mv=mv, res=res)
+
+        times = _timed_cpu(one, steps, warmup, budget_s)
+        med = _median(times)
+        return {"value": 1.0 / med, "cores": cores, "ms": med * 1e3, "extra": keep,
+                "sample": f"encode_B body (symbols + CDF indexes of both latents) of the bundled 1080p triple; median of "
+                          f"{len(times)} runs; oracle torch path, fp32"}
+
+    def parity(self, cpu):
+        import b200vc
+        with torch.no_grad():
+            mv, res = b200vc.encode_B_symbols(self.model, self.dev[2:3], self.dev[1:2], self.dev[0:1])
+        out = {}
+        tot = same = 0
+        for nm, a, b in (("mv", cpu["mv"], mv), ("res", cpu["res"], res)):
+            for k in ("y_symbols", "y_indexes", "z_symbols"):
+                eq = (a[k] == b[k].cpu()).float().mean().item()
+                out[f"{nm}_{k}_equal_frac"] = eq
+                tot += a[k].numel()
+                same += eq * a[k].numel()
+        out["symbols_equal_frac"] = same / tot
+        out["note"] = "free-running GPU (cuDNN) vs CPU (oneDNN); see tests/test_gpu_acceptance.py for the same-device bars"
+        return out
+
+
+# ------------------------------------------------------------------------- Flex-Rate GOP-16 (configs[2])
+def build_flex(device):
+    from b200vc import flexrate, synthetic
+    torch.manual_seed(0)
+    model = flexrate.BidirFlowRef(n=4, N=128).eval()
+    synthetic.calibrate_flex_(model, 0)
+    return model.to(device)
+
+
+class FlexGop16AllQ(Workload):
+    name = "flex_gop16_allq"
+    metric = "1080p B-frames/s encode+decode (Flex-Rate hierarchical GOP-16, all 8 rate points)"
+    scaling = "strong"
+    hot_kernels = ("gdn_f32", "warp_f32", "warp2_flex_f32", "blend_residual_f32", "gauss_cond_f32",
+                   "entropy_bottleneck_f32", "sse_u8_f32")
+
+    def __init__(self, args):
+        super().__init__(args)
+        from b200vc import gop
+        self.sched = gop.FLEX_GOP16
+        self.G = max(1, args.gops_per_step)
+        # units = (quality row, GOP); every rank sees the same GOPs (one shared sequence), sharded by unit
+        self.units = [(q, k) for q in range(len(gop.FLEX_QUALITIES)) for k in range(self.G)]
+
+    def setup(self, device, rank, world):
+        from b200vc import gop, synthetic
+        from b200vc.lhbdc import reflect_pad64
+        self.device, self.rank, self.world = device, rank, world
+        self.model = build_flex(device)
+        G = self.G
+        mine = gop.shard_units(len(self.units), world, rank)
+        self.my_units = [self.units[u] for u in mine]
+        self.my_ids = list(mine)
+        g = self.sched.gop
+        host = synthetic.make_sequence(G * g + 1, self.h, self.w, seed=1234)
+        self.host = pin(torch.stack([host[k * g:k * g + g + 1] for k in range(G)], 0))
+        self.dev = reflect_pad64(self.host.to(device).flatten(0, 1)).unflatten(0, (G, g + 1))
+        self.coders = {q: gop.GopCoder(self.model, self.sched, level_quality=gop.FLEX_QUALITIES[q][1])
+                       for q in {q for q, _ in self.my_units}}
+        nb = len(self.sched.refs)
+        self.b_idx = torch.tensor(sorted(self.sched.refs), device=device)
+        self.out_host = pin(torch.empty((max(1, len(self.my_units)), nb, 3, self.h, self.w)))
+        self.h2d_bytes = self.host.numel() * 4
+        self.d2h_bytes = len(self.my_units) * nb * (3 * self.h * self.w * 4 + 16)
+        self._last = None
+
+    def units_per_step(self):
+        return len(self.my_units) * len(self.sched.refs)
+
+    def total_units_per_step(self, world):
+        return len(self.units) * len(self.sched.refs)
+
+    def step(self, i, e2e):
+        from b200vc.lhbdc import reflect_pad64
+        g, h, w = self.sched.gop, self.h, self.w
+        x = self.dev
+        if e2e:
+            x = reflect_pad64(self.host.to(self.device, non_blocking=True).flatten(0, 1)).unflatten(0, (self.G, g + 1))
+        bits, sse = [], []
+        for j, (q, k) in enumerate(self.my_units):
+            if e2e:
+                b, s, dec = self.coders[q].code(x[k:k + 1], (h, w), want_decoded=True)
+                self.out_host[j].copy_(dec[0].index_select(0, self.b_idx)[..., :h, :w], non_blocking=True)
+            else:
+                b, s = self.coders[q].code(x[k:k + 1], (h, w))
+            bits.append(b)
+            sse.append(s)
+        self._last = (torch.cat(bits, 0), torch.cat(sse, 0)) if bits else None
+        if e2e and bits:
+            return torch.stack(self._last).to("cpu")
+        return None
+
+    def records(self, rank):
+        if self._last is None:
+            return torch.zeros((0, 4), dtype=torch.float64)
+        bits_c, sse_c = self._last[0].cpu(), self._last[1].cpu()
+        rec = []
+        for j, u in enumerate(self.my_ids):
+            for f in self.sched.order:
+                rec.append([float(u), float(f), bits_c[j, f].item(), sse_c[j, f].item()])
+        return torch.tensor(rec, dtype=torch.float64).reshape(-1, 4)
+
+    def config(self, world):
+        from b200vc import gop
+        per = [len(gop.shard_units(len(self.units), world, r)) for r in range(world)]
+        return {"workload": f"Flex-Rate-Hier-Bidir GOP-16 with motion refinement and per-level (n, l) bit allocation over "
+                            f"all 8 rate points, synthetic {self.w}x{self.h} (BASELINE.json configs[2])",
+                "step": f"{self.G} GOP-16 x 8 `qualities` rows = {len(self.units)} units of 15 B-frames, sharded over the "
+                        f"ranks ({per}); frames of a hierarchy level batched (1/2/4/8 per call)",
+                "weights": "random-init (seed 0) + deterministic calibration incl. gain matrices 1 + 0.1 randn",
+                "anchors": "uncoded source frames",
+                "conv_math": _conv_math(self.args),
+                "l2": "inputs larger than L2 (423 MB of frames + GBs of activations per unit)",
+                "parallelism": f"(quality, gop)-sharded x{world}",
+                "efficiency_expected": len(self.units) / (world * max(per)) if max(per) else None}
+
+    def cpu_sample(self, steps, warmup, budget_s):
+        from b200vc import gop, synthetic
+        from b200vc.lhbdc import reflect_pad64
+        from oracle import flexrate as o_flex
+        cores = _threads()
+        prod = build_flex("cpu")
+        orc = o_flex.BidirFlowRef(n=4, N=128).eval()
+        orc.load_state_dict(prod.state_dict())
+        frames = reflect_pad64(synthetic.make_sequence(17, self.h, self.w, seed=1234))
+        n, l = gop.FLEX_QUALITIES[3][1][0]
+        keep = {}
+
+        def one():
+            with torch.no_grad():
+                out = orc(frames[0:1], frames[8:9], frames[16:17], n=[n], l=l, train=False)
+            keep.update(size=out["size"].item(), x_hat=out["x_hat"])
+
+        times = _timed_cpu(one, steps, warmup, budget_s)
+        med = _median(times)
+        return {"value": 1.0 / med, "cores": cores, "ms": med * 1e3, "extra": keep,
+                "sample": f"level-0 B-frame (frame 8, refs 0/16) of a GOP-16 at quality row 3 (n={n}, l={l}), padded "
+                          f"{frames.shape[2]}x{frames.shape[3]}; median of {len(times)} runs; oracle torch path, fp32"}
+
+    def parity(self, cpu):
+        from b200vc import gop
+        n, l = gop.FLEX_QUALITIES[3][1][0]
+        x = self.dev[0]
+        with torch.no_grad():
+            x_hat, bits = self.model.forward_device(x[0:1], x[8:9], x[16:17], [n], l)[:2]
+        dx = (x_hat.cpu() - cpu["x_hat"]).abs()
+        return {"frame": "GOP 0, frame 8 (refs 0 and 16), quality row 3", "bits_gpu": bits.item(),
+                "bits_cpu_oracle": cpu["size"], "bits_rel": abs(bits.item() - cpu["size"]) / cpu["size"],
+                "x_hat_max_abs_diff": dx.max().item(), "x_hat_frac_within_1e-3": (dx < 1e-3).float().mean().item(),
+                "note": "free-running GPU (cuDNN) vs CPU (oneDNN)"}
+
+
+# -------------------------------------------------------------------------- ICIP2024 GOP-16 (configs[3])
+class IcipGop16(Workload):
+    name = "icip_gop16"
+    metric = "1080p B-frames/s encode+decode (ICIP2024 FlowGuidedB, GOP-16, down-ratio search)"
+    hot_kernels = ("gdn_f32", "warp_f32", "warp2_half_sse_f32", "deform_conv2d_f32", "gauss_cond_f32",
+                   "entropy_bottleneck_f32", "round_checker_f32", "checker_mask_f32", "sse_u8_f32")
+
+    def setup(self, device, rank, world):
+        from b200vc import flowguided, synthetic
+        from b200vc.lhbdc import reflect_pad64
+        self.device, self.rank, self.world = device, rank, world
+        torch.manual_seed(0)
+        self.model = flowguided.FlowGuidedB().eval()
+        flowguided.calibrate_(self.model, 0)
+        self.model.to(device)
+        self.levels = list(range(5))[rank::world] if world > 1 else list(range(5))
+        host = synthetic.make_sequence(17, self.h, self.w, seed=1234 + rank)
+        self.host = pin(host)
+        self.dev = reflect_pad64(self.host.to(device))
+        self.coder = flowguided.SequenceCoder(self.model, gop=16)
+        self.out_host = pin(torch.empty((15, 3, self.h, self.w)))
+        self.h2d_bytes = self.host.numel() * 4
+        self.d2h_bytes = len(self.levels) * 15 * (3 * self.h * self.w * 4 + 16)
+        self._last = None
+
+    def units_per_step(self):
+        return 15 * len(self.levels)
+
+    def total_units_per_step(self, world):
+        return 15 * 5
+
+    scaling = "strong"
+
+    def step(self, i, e2e):
+        from b200vc.lhbdc import reflect_pad64
+        x = reflect_pad64(self.host.to(self.device, non_blocking=True)) if e2e else self.dev
+        rec = []
+        for s in self.levels:
+            bits, sse, ratios, dec = self.coder.code(x, (self.h, self.w), s, want_decoded=e2e)
+            if e2e:
+                self.out_host.copy_(dec[1:16, :, :self.h, :self.w], non_blocking=True)
+            rec.append((s, bits, sse))
+        self._last = rec
+        if e2e and rec:
+            return torch.stack([torch.stack([b, q]) for _, b, q in rec]).to("cpu")
+        return None
+
+    def records(self, rank):
+        rec = []
+        for s, bits, sse in self._last or []:
+            b, q = bits.cpu(), sse.cpu()
+            for f in range(1, 16):
+                rec.append([float(s), float(f), b[f].item(), q[f].item()])
+        return torch.tensor(rec, dtype=torch.float64).reshape(-1, 4)
+
+    def config(self, world):
+        return {"workload": f"ICIP2024 FlowGuidedB (flow-guided deformable alignment, ELIC-style checkerboard context "
+                            f"entropy model, per-frame down-ratio search over {{1,2,4,8,16}}), GOP-16, synthetic "
+                            f"{self.w}x{self.h} (BASELINE.json configs[3])",
+                "step": f"one GOP-16 (15 B-frames) at each of the 5 rate levels s, levels sharded over the ranks",
+                "weights": "random-init (seed 0) + deterministic calibration",
+                "anchors": "uncoded source frames",
+                "conv_math": _conv_math(self.args),
+                "l2": "inputs larger than L2",
+                "parallelism": f"level-sharded x{world}"}
+
+    def cpu_sample(self, steps, warmup, budget_s):
+        from b200vc import flowguided, synthetic
+        from b200vc.lhbdc import reflect_pad64
+        from oracle import flowguided as o_fg
+        cores = _threads()
+        torch.manual_seed(0)
+        prod = flowguided.FlowGuidedB().eval()
+        flowguided.calibrate_(prod, 0)
+        orc = o_fg.FlowGuidedB().eval()
+        orc.load_state_dict(prod.state_dict())
+        frames = reflect_pad64(synthetic.make_sequence(17, self.h, self.w, seed=1234))
+        keep = {}
+
+        def one():
+            with torch.no_grad():
+                out = o_fg.code_frame(orc, frames[0:1], frames[16:17], frames[8:9], 0.5, 0.5, s=2)
+            keep.update(bits=out["bits"], ratio=out["down_ratio"])
+
+        times = _timed_cpu(one, steps, warmup, budget_s)
+        med = _median(times)
+        return {"value": 1.0 / med, "cores": cores, "ms": med * 1e3, "extra": keep,
+                "sample": f"level-0 B-frame (frame 8, refs 0/16) at rate level s=2 incl. its 5-ratio search; median of "
+                          f"{len(times)} runs; oracle torch path, fp32"}
+
+    def parity(self, cpu):
+        from b200vc import flowguided
+        x = self.dev
+        with torch.no_grad():
+            out = flowguided.code_frame(self.model, x[0:1], x[16:17], x[8:9], 0.5, 0.5, s=2)
+        bits = float(out["bits"])
+        return {"frame": "frame 8 (refs 0 and 16), s=2", "bits_gpu": bits, "bits_cpu_oracle": cpu["bits"],
+                "bits_rel": abs(bits - cpu["bits"]) / cpu["bits"], "down_ratio_gpu": out["down_ratio"],
+                "down_ratio_cpu_oracle": cpu["ratio"], "note": "free-running GPU (cuDNN) vs CPU (oneDNN)"}
+
+
+# ------------------------------------------------------------------------ OJSP2025 ratio search (configs[4])
+class FlowStub(nn.Module):
+    """Stand-in for DCVC-FM's ``optic_flow`` (its source is absent from the reference tree: SURVEY 2.3): a small
+    seeded conv net with the same call signature, so every candidate ratio yields a different, smooth motion field."""
+
+    def __init__(self):
+        super().__init__()
+        g = torch.Generator().manual_seed(7)
+        self.c1 = nn.Conv2d(6, 16, 5, padding=2)
+        self.c2 = nn.Conv2d(16, 2, 5, padding=2)
+        with torch.no_grad():
+            for p in self.parameters():
+                p.copy_(0.2 * torch.randn(p.shape, generator=g))
+
+    def optic_flow(self, cur, ref):
+        return 6.0 * torch.tanh(self.c2(F.relu(self.c1(torch.cat([cur, ref], 1)))))
+
+
+class OjspSearch4k(Workload):
+    name = "ojsp_search_4k"
+    metric = "4K frames/s down-sampling-ratio search (OJSP2025: 32 candidate ratios, warp + PSNR each)"
+    unit = "frames/s"
+    hot_kernels = ("warp_sse_f32",)
+
+    def setup(self, device, rank, world):
+        from b200vc import synthetic
+        self.device = device
+        self.model = FlowStub().eval().to(device)
+        # intra-period-16 segments are the shards: every rank searches frames of its own segment
+        host = synthetic.make_sequence(3, self.h, self.w, seed=1234 + rank)
+        self.host = pin(host)
+        self.dev = self.host.to(device)
+        self.mv_host = pin(torch.empty((1, 2, self.h, self.w)))
+        self.h2d_bytes = 2 * 3 * self.h * self.w * 4
+        self.d2h_bytes = 2 * self.h * self.w * 4 + 8
+        self._last = None
+
+    def units_per_step(self):
+        return 1
+
+    def step(self, i, e2e):
+        from b200vc import ojsp
+        k = i % 2
+        with torch.no_grad():
+            if e2e:
+                pair = self.host[k:k + 2].to(self.device, non_blocking=True)
+            else:
+                pair = self.dev[k:k + 2]
+            dpb = {"ref_frame": pair[0:1], "ref_down_ratio": 1}
+            mv, ratio = ojsp.optimize_down_sampling_ratio(self.model, pair[1:2], dpb)
+            if e2e:
+                self.mv_host.copy_(mv, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+        self._last = ratio
+        return None
+
+    def records(self, rank):
+        return torch.tensor([[float(rank), 0.0, float(self._last), 0.0]], dtype=torch.float64)
+
+    def config(self, world):
+        return {"workload": f"OJSP2025 video_model down-sampling-ratio search (DMC.optimize_down_sampling_ratio: 32 ratios, "
+                            f"warp + PSNR per candidate), synthetic {self.w}x{self.h} (BASELINE.json configs[4]; the rest "
+                            "of DCVC-FM is absent from the reference tree)",
+                "step": "one P-frame: 32 x (antialiased down-sample, flow stand-in, up-sample, fused warp+SSE), one host sync",
+                "flow_estimator": "seeded 2-layer conv stand-in (DCVC-FM's ME net is not in the reference tree)",
+                "conv_math": _conv_math(self.args),
+                "l2": "each candidate streams 2 x 99.5 MB frames + a 66 MB field (> L2 over the 32 candidates)",
+                "parallelism": f"segment-sharded x{world}"}
+
+    def cpu_sample(self, steps, warmup, budget_s):
+        from b200vc import synthetic
+        from oracle import ojsp as o_ojsp
+        cores = _threads()
+        model = FlowStub().eval()
+        f = synthetic.make_sequence(3, self.h, self.w, seed=1234)
+        keep = {}
+
+        def one():
+            with torch.no_grad():
+                mv, ratio, psnr = o_ojsp.optimize_down_sampling_ratio(model, f[1:2], {"ref_frame": f[0:1], "ref_down_ratio": 1})
+            keep.update(ratio=ratio, psnr=psnr)
+
+        times = _timed_cpu(one, steps, warmup, budget_s)
+        med = _median(times)
+        return {"value": 1.0 / med, "cores": cores, "ms": med * 1e3, "extra": keep,
+                "sample": f"one {self.w}x{self.h} P-frame's full 32-ratio search; median of {len(times)} runs; oracle torch "
+                          "path (grid_sample warp + torch PSNR), fp32"}
+
+    def parity(self, cpu):
+        from b200vc import ojsp
+        with torch.no_grad():
+            x, ref = self.dev[1:2], self.dev[0:1]
+            psnr = torch.stack([ojsp.warp_psnr(ref, ojsp.candidate_flow(self.model, x, ref, r), x)
+                                for r in ojsp.DOWNSAMPLING_RATIOS]).float().cpu()
+            _, ratio = ojsp.optimize_down_sampling_ratio(self.model, x, {"ref_frame": ref, "ref_down_ratio": 1})
+        return {"ratio_gpu": ratio, "ratio_cpu_oracle": cpu["ratio"],
+                "psnr_max_abs_diff_db": (psnr - cpu["psnr"].float()).abs().max().item(),
+                "note": "free-running GPU vs CPU (the flow stand-in's convolutions differ by backend)"}
+
+
+REGISTRY = {c.name: c for c in (LhbdcGop8, LhbdcFrames, FlexGop16AllQ, IcipGop16, OjspSearch4k)}
 
 
 # --------------------------------------------------------------------------------------- reference arm
@@ -190,28 +883,36 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return 0
+    wl = REGISTRY[args.workload](args)
     steps, warmup = max(1, args.steps), max(0, args.warmup)
-    value, cores, sample, ms = cpu_reference_frames_per_s(args, steps, warmup, args.cpu_budget_s)
+    r = wl.cpu_sample(steps, warmup, args.cpu_budget_s)
+    world = int(os.environ.get("WORLD_SIZE", args.gpus))
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"LHBDC hierarchical GOP-8 B-frame encode/decode, synthetic {args.width}x{args.height}, "
-                               "random-init calibrated weights", "step": "one B-frame (bounded CPU sample)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": wl.metric, "value": r["value"], "unit": wl.unit, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": r["ms"], "higher_is_better": True, "scaling": wl.scaling,
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_of(wl, args, world),
+        "cpu_baseline": {"value": r["value"], "unit": wl.unit, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": wl.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
     return 0
 
 
+def config_of(wl, args, world):
+    """The ``config`` dict is built the same way in both arms (the driver compares them)."""
+    try:
+        c = dict(wl.config(world))
+    except Exception:
+        c = {"workload": wl.name}
+    c.setdefault("workload", wl.name)
+    return c
+
+
 # ----------------------------------------------------------------------------------------- product arm
 def run_product(args):
-    import b200vc
     from b200vc import dist as bd
-    from b200vc import gop, ops, synthetic
-    from b200vc.lhbdc import reflect_pad64
+    from b200vc import gop, ops
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: the b200vc arm needs a CUDA device (there is no CPU fallback); "
@@ -226,89 +927,74 @@ def run_product(args):
     torch.backends.cudnn.benchmark = True  # as LHBDC/test/testing.py:31
 
     steps, warmup = max(1, args.steps), max(3, args.warmup)
-    G, sched = max(1, args.gops_per_step), gop.LHBDC_GOP8
-    h, w = args.height, args.width
-    model = build_product_model(device)
-    coder = gop.GopCoder(model, sched)
+    wl = REGISTRY[args.workload](args)
+    wl.setup(device, rank, world)
+    whole_sequence = bool(getattr(wl, "T", 0))
 
-    # two distinct GOP batches per rank, alternated across steps; one batch = G*9 frames = G*224 MB > L2
-    n_sets = 2
-    host = synthetic.make_sequence(n_sets * G * sched.gop + 1, h, w, seed=1234 + rank)
-    idx = [[k * sched.gop + t for t in range(sched.gop + 1)] for k in range(n_sets * G)]
-    host_sets = [torch.stack([host[idx[s * G + g]] for g in range(G)], 0).pin_memory() for s in range(n_sets)]
-    dev_sets = [reflect_pad64(hs.to(device).flatten(0, 1)).unflatten(0, (G, sched.gop + 1)) for hs in host_sets]
-    frames_per_step = G * len(sched.refs)
-
-    def step_resident(i):
-        return coder.code(dev_sets[i % n_sets], (h, w))
-
-    def step_e2e(i):
-        x = host_sets[i % n_sets].to(device, non_blocking=True)                       # H2D (pinned)
-        x = reflect_pad64(x.flatten(0, 1)).unflatten(0, (G, sched.gop + 1))
-        bits, sse = coder.code(x, (h, w))
-        out = torch.stack([bits, sse]).to("cpu", non_blocking=False)                  # D2H of the step's result
-        return out
-
-    for i in range(warmup):
-        step_resident(i)
-    torch.cuda.synchronize()
-
-    # ---- timed region 1: resident inputs, per-kernel CUDA events recorded live ------------------------
-    launches0 = ops.launch_count()
-    bd.barrier()
-    torch.cuda.synchronize()
-    with ClockSampler(local_rank) as clocks:
-        ops.profile_begin()
-        if args.ncu_range:
-            torch.cuda.profiler.start()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        for i in range(steps):
-            bits, sse = step_resident(i)
-        ev1.record()
+    with torch.no_grad():
+        for i in range(warmup):
+            wl.step(i, False)
         torch.cuda.synchronize()
-        if args.ncu_range:
-            torch.cuda.profiler.stop()
-        prof = ops.profile_end()
+
+        # ---- timed region 1: resident inputs, per-kernel CUDA events recorded live ------------------------
+        launches0 = ops.launch_count()
         bd.barrier()
-    ms_total = bd.max_over_ranks(ev0.elapsed_time(ev1), device)
-    launches = ops.launch_count() - launches0
-    clock_summary = clocks.summary()
+        torch.cuda.synchronize()
+        with ClockSampler(local_rank) as clocks:
+            ops.profile_begin()
+            if args.ncu_range:
+                torch.cuda.profiler.start()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for i in range(steps):
+                wl.step(i, False)
+            ev1.record()
+            torch.cuda.synchronize()
+            if args.ncu_range:
+                torch.cuda.profiler.stop()
+            prof = ops.profile_end()
+            bd.barrier()
+        ms_total = bd.max_over_ranks(ev0.elapsed_time(ev1), device)
+        launches = ops.launch_count() - launches0
+        clock_summary = clocks.summary()
+        rec_local = wl.records(rank)
 
-    # ---- timed region 2: end to end from pinned host memory ------------------------------------------
-    for i in range(2):
-        step_e2e(i)
-    bd.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for i in range(steps):
-        res = step_e2e(i)
-    ev1.record()
-    torch.cuda.synchronize()
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    bd.barrier()
-    e2e_ms = bd.max_over_ranks(max(ev0.elapsed_time(ev1), wall_ms), device)
-    h2d = host_sets[0].numel() * 4
-    d2h = res.numel() * 8
+        # ---- timed region 2: end to end from pinned host memory ------------------------------------------
+        e2e_ms = None
+        if not args.no_e2e:
+            for i in range(1 if whole_sequence else 2):
+                wl.step(i, True)
+            bd.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for i in range(steps):
+                wl.step(i, True)
+            ev1.record()
+            torch.cuda.synchronize()
+            wall_ms = (time.perf_counter() - t0) * 1e3
+            bd.barrier()
+            e2e_ms = bd.max_over_ranks(max(ev0.elapsed_time(ev1), wall_ms), device)
 
-    # ---- records: gather per-frame (gop, frame, bits, sse) over ranks; totals in global frame order ----
-    rec = []
-    bits_c, sse_c = bits.cpu(), sse.cpu()
-    for g in range(G):
-        for f in sched.order:
-            rec.append([float(rank * G + g), float(f), bits_c[g, f].item(), sse_c[g, f].item()])
-    table = bd.gather_records(torch.tensor(rec, dtype=torch.float64, device=device))
-    tot = bd.totals(table)
-    n_frames = table.shape[0]
-    bpp = tot[0].item() / (n_frames * h * w)
-    psnr = gop.psnr_from_sse(table[:, 3].cpu(), 3 * h * w).mean().item()
+    # ---- records: gather per-frame (unit, frame, bits, sse) over ranks; totals in global frame order ----
+    quality = None
+    if rec_local is not None:
+        table = bd.gather_records(rec_local.to(device))
+        if table.shape[0]:
+            tot = bd.totals(table)
+            n_frames = table.shape[0]
+            quality = {"frames": n_frames, "total_bits": tot[0].item(),
+                       "bpp": tot[0].item() / (n_frames * wl.h * wl.w)}
+            if (table[:, 3] > 0).all():
+                quality["psnr_db"] = gop.psnr_from_sse(table[:, 3].cpu(), 3 * wl.h * wl.w).mean().item()
+            import hashlib
+            quality["bits_sha256"] = hashlib.sha256(table[:, 2].cpu().numpy().tobytes()).hexdigest()[:16]
 
     if rank == 0:
         W_ = bd.world_size()
-        value = frames_per_step * steps * W_ / (ms_total / 1e3)
-        e2e_value = frames_per_step * steps * W_ / (e2e_ms / 1e3)
+        total_units = wl.total_units_per_step(W_)
+        value = total_units * steps / (ms_total / 1e3)
         peak, peak_src = measured_peak()
         kernels = {}
         for name, r in prof.items():
@@ -321,7 +1007,7 @@ def run_product(args):
                     t: {"launches": v["launches"], "us_per_launch": 1e3 * v["ms"] / v["launches"],
                         "GBps": v["bytes"] / (v["ms"] / 1e3) / 1e9 if v["ms"] > 0 else None}
                     for t, v in r["by_shape"].items()}
-        hot = {k: v for k, v in kernels.items() if k in HOT_KERNELS}
+        hot = {k: v for k, v in kernels.items() if k in wl.hot_kernels}
         dom = max(hot, key=lambda k: hot[k]["ms_per_step"]) if hot else None
         hot_ms = sum(v["ms_per_step"] for v in hot.values())
         hot_bytes = sum(v["algorithmic_MB_per_step"] for v in hot.values()) * 1e6
@@ -335,32 +1021,27 @@ def run_product(args):
                         "hot_path_ms_per_step": hot_ms, "hot_path_GBps": hot_bytes / (hot_ms / 1e3) / 1e9 if hot_ms else None,
                         "hot_path_share_of_step": hot_ms / (ms_total / steps)}
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": W_, "steps": steps, "warmup": warmup,
-            "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {
-                "workload": f"LHBDC hierarchical GOP-8 B-frame encode/decode, synthetic {w}x{h}, 1 B200 per rank "
-                            "(BASELINE.json configs[1])",
-                "step": f"{G} GOP-8 per GPU = {frames_per_step} B-frames, levels batched (1/2/4 frames per call)",
-                "weights": "random-init (seed 0) + deterministic calibration (b200vc/synthetic.py)",
-                "anchors": "uncoded source frames (I-frame codec is outside the B-frame hot path)",
-                "conv_math": "cuDNN TF32 allowed (torch default, as the reference runs)" if args.conv_tf32
-                             else "cuDNN fp32 (allow_tf32=False): the configuration parity is proven in",
-                "l2": "inputs larger than L2: each step streams >= 224 MB of frames + GBs of activations; "
-                      "two GOP sets alternate",
-                "parallelism": f"gop-sharded x{W_}",
-            },
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms / steps},
+            "metric": wl.metric, "value": value, "unit": wl.unit, "n_gpus": W_, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": wl.scaling, "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config_of(wl, args, W_),
+            "e2e": None if e2e_ms is None else {
+                "value": total_units * steps / (e2e_ms / 1e3), "unit": wl.unit, "h2d_bytes_per_step": wl.h2d_bytes,
+                "d2h_bytes_per_step": wl.d2h_bytes, "ms_per_step": e2e_ms / steps,
+                "returns": "decoded frames (fp32, unpadded crop) + per-frame bits and SSE to pinned host memory"},
             "gpu_launches": launches,
             "clocks": clock_summary,
             "roofline": roofline,
             "kernels": kernels,
-            "quality": {"bpp": bpp, "psnr_db": psnr, "frames": n_frames, "total_bits": tot[0].item()},
+            "quality": quality,
         }
         if W_ == 1 and not args.no_cpu_baseline:
-            v, cores, sample, _ = cpu_reference_frames_per_s(args, 1, 0, 120.0)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+            r = wl.cpu_sample(1, 0, 120.0)
+            line["cpu_baseline"] = {"value": r["value"], "unit": wl.unit, "cores": r["cores"], "kind": "port",
+                                    "sample": r["sample"]}
+            try:
+                line["parity"] = wl.parity(r["extra"])
+            except Exception as exc:  # the timing line must not be lost to a parity-leg error
+                line["parity"] = {"error": f"{type(exc).__name__}: {exc}"}
         emit(line)
     bd.barrier()
     if torch.distributed.is_initialized():
@@ -370,7 +1051,7 @@ def run_product(args):
 
 def load_traffic(kernel):
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the kernel from the committed
-    `ncu --set full` capture (profiles/traffic.json, profiles/r01_ncu_summary.md), or None."""
+    `ncu --set full` capture (profiles/traffic.json), or None."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             entry = json.load(f).get(kernel)

@@ -105,7 +105,8 @@ B200VC_API int b200vc_warp2_lhbdc_f32(const float* x_before, const float* x_afte
 B200VC_API int b200vc_warp2_half_sse_blocks(int H, int W);
 B200VC_API int b200vc_warp2_half_sse_f32(const float* x1, const float* x2, const float* flow1, const float* flow2,
                                          const float* x_cur, const float* tab_x, const float* tab_y, float* pred,
-                                         double* partials, int N, int H, int W, int variant, void* stream);
+                                         double* partials, double* totals, int32_t* counters, int N, int H, int W,
+                                         int variant, void* stream);
 
 /* Single-reference search form (OJSP2025/video_model.py:621-666: x_hat = self.warp(ref_frame, est_mv);
  * PSNR(x, x_hat) per candidate down-sampling ratio): warp + squared error against x_cur, no clamp.
@@ -113,8 +114,8 @@ B200VC_API int b200vc_warp2_half_sse_f32(const float* x1, const float* x2, const
  *   partials double[N * b200vc_warp2_half_sse_blocks(H, W)] as above.
  */
 B200VC_API int b200vc_warp_sse_f32(const float* img, const float* flow, const float* x_cur, const float* tab_x,
-                                   const float* tab_y, float* pred, double* partials, int N, int H, int W,
-                                   int variant, void* stream);
+                                   const float* tab_y, float* pred, double* partials, double* totals,
+                                   int32_t* counters, int N, int H, int W, int variant, void* stream);
 
 /* ------------------------------------------------------------------------------ SPyNet glue
  * Replaces the non-convolutional part of Network.forward (LHBDC/model/flow.py:78-101).
@@ -168,11 +169,13 @@ B200VC_API int b200vc_checker_mask_f32(const float* src, int64_t src_bs, float* 
  *   a, b: the two warped references [N,3,H,W] (batch strides a_bs, b_bs: may be halves of the concat
  *   buffer); mask [N,1|2,H,W] (NULL for BLEND_HALF); x_cur [N,3,H,W]; pred, res (each nullable) [N,3,H,W].
  *   sse_partials (nullable, double[N*n_blocks]) receives per-CTA sums of (clamp(pred,0,1) - x_cur)^2 -- the
- *   search form only needs that scalar; reduce with b200vc_sum_partials_f64.  n_blocks = CTAs per sample.
+ *   search form only needs that scalar; reduce with b200vc_sum_partials_f64, or pass sse_totals / counters (see
+ *   "fused finish" below).  n_blocks = CTAs per sample.
  */
 B200VC_API int b200vc_blend_residual_f32(int mode, const float* mask, const float* a, int64_t a_bs, const float* b,
                               int64_t b_bs, const float* x_cur, float* pred, float* res,
-                              double* sse_partials, int n_blocks, int N, int H, int W, void* stream);
+                              double* sse_partials, int n_blocks, double* sse_totals, int32_t* counters, int N,
+                              int H, int W, void* stream);
 
 /* ------------------------------------------------------------------------------------------ GDN / IGDN
  * Replaces compressai.layers.GDN.forward (instantiated at LHBDC/model/layers.py:49-53,84-88,124-128,159-163).
@@ -211,12 +214,17 @@ B200VC_API void b200vc_debug_set_gdn_trace(long long* device_buffer);
  *   scale_table [n_table] (needed iff indexes != NULL);
  *   bits_partials (nullable) double[N * blocks_per_sample]: per-CTA sums of -log2(lik); the grid is
  *   blocks_per_sample x N (use b200vc_reduce_blocks(C*HW)).
+ *   Fused finish (every kernel that writes per-CTA partials has this pair): totals (nullable) double[N] + counters
+ *   int32[N], counters ZERO on entry.  The CTA that finishes last for a sample sums that sample's partials in the
+ *   same fixed order as b200vc_sum_partials_f64 (bit-identical result, independent of scheduling), writes totals[n]
+ *   and leaves the counter zero again -- the separate reduction launch (the reference's `torch.log(lik).sum()`
+ *   second pass, LHBDC/model/m.py:73-91) disappears.  totals == NULL keeps the two-launch form.
  */
 B200VC_API int b200vc_gauss_cond_f32(const float* y, const float* scales, const float* means, int64_t sm_bs,
                           const float* inv_gain, float* y_hat, float* lik, int32_t* symbols,
                           int32_t* indexes, const float* scale_table, int n_table, float scale_bound,
-                          float lik_bound, double* bits_partials, int blocks_per_sample, int N, int C,
-                          int64_t HW, void* stream);
+                          float lik_bound, double* bits_partials, int blocks_per_sample, double* bits_totals,
+                          int32_t* counters, int N, int C, int64_t HW, void* stream);
 
 /* ------------------------------------------------------------------------ factorised prior (Q3, Q4, Q5)
  * Replaces EntropyBottleneck.forward (eval) (LHBDC/model/layers.py:97-98 call sites).
@@ -229,12 +237,12 @@ B200VC_API int b200vc_eb_prepare_f32(const float* const* matrices /*[host] 5 dev
                           const float* quantiles /*[C,1,3]*/, float* packed /*[C,59]*/, int C, void* stream);
 /*   z [N,C,HW]; gain / inv_gain (nullable) [C] (Flex hyper_gain_unit / hyper_inv_gain_unit);
  *   z_hat, lik (nullable) [N,C,HW]; symbols (nullable int32): round(z*gain - median);
- *   bits_partials as above.
+ *   bits_partials / bits_totals / counters as above.
  */
 B200VC_API int b200vc_entropy_bottleneck_f32(const float* z, const float* packed, const float* gain,
                                   const float* inv_gain, float* z_hat, float* lik, int32_t* symbols,
-                                  float lik_bound, double* bits_partials, int blocks_per_sample, int N,
-                                  int C, int64_t HW, void* stream);
+                                  float lik_bound, double* bits_partials, int blocks_per_sample,
+                                  double* bits_totals, int32_t* counters, int N, int C, int64_t HW, void* stream);
 
 /* out[s] = sum_{k < n_per} partials[s*n_per + k] in fixed order (deterministic: 1-GPU and N-GPU totals agree). */
 B200VC_API int b200vc_sum_partials_f64(const double* partials, int n_per, int n_out, double* out, void* stream);
@@ -242,10 +250,10 @@ B200VC_API int b200vc_sum_partials_f64(const double* partials, int n_per, int n_
 /* -------------------------------------------------------------------------------------------- metrics
  * Replaces the D2H + numpy PSNR of LHBDC/test/testing.py:176-182: sum over the unpadded crop [:h,:w] of
  * (round(clip(a)*255) - round(clip(b)*255))^2 PER SAMPLE, as partials[N][n_blocks] per-CTA doubles (exact integers;
- * reduce with b200vc_sum_partials_f64(partials, n_blocks, N, out)).
+ * reduce with b200vc_sum_partials_f64(partials, n_blocks, N, out), or pass totals / counters: fused finish).
  */
-B200VC_API int b200vc_sse_u8_f32(const float* a, const float* b, double* partials, int n_blocks, int N, int C,
-                      int H, int W, int h, int w, void* stream);
+B200VC_API int b200vc_sse_u8_f32(const float* a, const float* b, double* partials, int n_blocks, double* totals,
+                      int32_t* counters, int N, int C, int H, int W, int h, int w, void* stream);
 
 /* ------------------------------------------------------------------------------------- rANS
  * Replaces the CPU coder behind `.compress()` / `.decompress()` (compressai.ans BufferedRansEncoder.encode_with_indexes

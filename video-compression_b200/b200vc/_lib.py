@@ -26,23 +26,23 @@ _SIGNATURES = {
     "b200vc_warp_f32": (c_int, [_fp, c_int64, _fp, _fp, _fp, _fp, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "b200vc_warp2_lhbdc_f32": (c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "b200vc_warp2_half_sse_blocks": (c_int, [c_int, c_int]),
-    "b200vc_warp2_half_sse_f32": (c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, c_int, c_int, c_int, c_int, c_void_p]),
-    "b200vc_warp_sse_f32": (c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, c_int, c_int, c_int, c_int, c_void_p]),
+    "b200vc_warp2_half_sse_f32": (c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, c_int, c_int, c_int, c_int, c_void_p]),
+    "b200vc_warp_sse_f32": (c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, c_int, c_int, c_int, c_int, c_void_p]),
     "b200vc_deform_conv2d_f32": (c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp] + [c_int] * 15 + [c_void_p]),
     "b200vc_round_checker_f32": (c_int, [_fp, _fp, _fp, c_int, c_int, c_int, c_int, c_void_p]),
     "b200vc_checker_mask_f32": (c_int, [_fp, c_int64, _fp, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "b200vc_spynet_pyramid_f32": (c_int, [_fp, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "b200vc_spynet_level_f32": (c_int, [_fp, c_int64, _fp, c_int64, _fp, _fp, _fp, _fp, c_int, c_int, c_int, c_int, c_int, c_void_p]),
-    "b200vc_blend_residual_f32": (c_int, [c_int, _fp, _fp, c_int64, _fp, c_int64, _fp, _fp, _fp, _fp, c_int, c_int, c_int, c_int, c_void_p]),
+    "b200vc_blend_residual_f32": (c_int, [c_int, _fp, _fp, c_int64, _fp, c_int64, _fp, _fp, _fp, _fp, c_int, _fp, _fp, c_int, c_int, c_int, c_void_p]),
     "b200vc_gdn_params_floats": (c_int64, [c_int]),
     "b200vc_gdn_prepare_f32": (c_int, [_fp, _fp, c_float, c_float, c_float, _fp, c_int, c_void_p]),
     "b200vc_gdn_f32": (c_int, [_fp, _fp, _fp, _fp, c_int, c_int, c_int64, c_int, c_int, c_void_p]),
     "b200vc_debug_set_gdn_trace": (None, [_fp]),
-    "b200vc_gauss_cond_f32": (c_int, [_fp, _fp, _fp, c_int64, _fp, _fp, _fp, _fp, _fp, _fp, c_int, c_float, c_float, _fp, c_int, c_int, c_int, c_int64, c_void_p]),
+    "b200vc_gauss_cond_f32": (c_int, [_fp, _fp, _fp, c_int64, _fp, _fp, _fp, _fp, _fp, _fp, c_int, c_float, c_float, _fp, c_int, _fp, _fp, c_int, c_int, c_int64, c_void_p]),
     "b200vc_eb_prepare_f32": (c_int, [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), _fp, _fp, c_int, c_void_p]),
-    "b200vc_entropy_bottleneck_f32": (c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, c_float, _fp, c_int, c_int, c_int, c_int64, c_void_p]),
+    "b200vc_entropy_bottleneck_f32": (c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, c_float, _fp, c_int, _fp, _fp, c_int, c_int, c_int64, c_void_p]),
     "b200vc_sum_partials_f64": (c_int, [_fp, c_int, c_int, _fp, c_void_p]),
-    "b200vc_sse_u8_f32": (c_int, [_fp, _fp, _fp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "b200vc_sse_u8_f32": (c_int, [_fp, _fp, _fp, c_int, _fp, _fp, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "b200vc_rans_scratch_words": (c_int, [c_int]),
     "b200vc_rans_encode": (c_int, [_fp, _fp, _fp, _fp, _fp, c_int, c_int64, c_int, _fp, _fp, c_void_p]),
     "b200vc_rans_compact": (c_int, [_fp, c_int, _fp, _fp, c_int, _fp, c_void_p]),

@@ -249,10 +249,11 @@ def warp2_half_sse(x1, x2, flow1, flow2, x_cur, variant="ac1", want_pred=False):
     part = torch.empty(N * nb, device=x1.device, dtype=torch.float64)
     pred = torch.empty_like(x1) if want_pred else None
     p = lambda t: t.data_ptr() if t is not None else None
+    tot, cnt = _finish(x1.device, N)
     _run("warp2_half_sse_f32", (13 + 3 * int(want_pred)) * 4 * N * H * W, lambda: lib.b200vc_warp2_half_sse_f32(
         x1.data_ptr(), x2.data_ptr(), f1.data_ptr(), f2.data_ptr(), xc.data_ptr(), p(tx), p(ty), p(pred),
-        part.data_ptr(), N, H, W, _VARIANTS[variant], _stream()))
-    return sum_partials(part, nb, N), pred
+        part.data_ptr(), p(tot), p(cnt), N, H, W, _VARIANTS[variant], _stream()))
+    return (tot if tot is not None else sum_partials(part, nb, N)), pred
 
 
 def warp_sse(img, flow, x_cur, variant="ac1", want_pred=False):
@@ -271,10 +272,11 @@ def warp_sse(img, flow, x_cur, variant="ac1", want_pred=False):
     part = torch.empty(N * nb, device=img.device, dtype=torch.float64)
     pred = torch.empty_like(img) if want_pred else None
     p = lambda t: t.data_ptr() if t is not None else None
+    tot, cnt = _finish(img.device, N)
     _run("warp_sse_f32", (8 + 3 * int(want_pred)) * 4 * N * H * W, lambda: lib.b200vc_warp_sse_f32(
-        img.data_ptr(), flow.data_ptr(), xc.data_ptr(), p(tx), p(ty), p(pred), part.data_ptr(), N, H, W,
+        img.data_ptr(), flow.data_ptr(), xc.data_ptr(), p(tx), p(ty), p(pred), part.data_ptr(), p(tot), p(cnt), N, H, W,
         _VARIANTS[variant], _stream()), tag=f"{N}x3x{H}x{W}")
-    return sum_partials(part, nb, N), pred
+    return (tot if tot is not None else sum_partials(part, nb, N)), pred
 
 
 # --------------------------------------------------------------------- checkerboard context glue
@@ -369,6 +371,24 @@ def reduce_blocks(elems_per_sample):
     return _lib.load().b200vc_reduce_blocks(int(elems_per_sample))
 
 
+_FUSED_FINISH = os.environ.get("B200VC_FUSED_FINISH", "1") != "0"
+_counters = {}
+
+
+def _finish(dev, n_out):
+    """(totals[n_out] float64, counters int32) for the kernels' fused last-CTA-done reduction, or (None, None) when
+    switched off (B200VC_FUSED_FINISH=0: the two-launch form through ``sum_partials``).  The ticket counters are one
+    zeroed buffer per (device, stream): launches on a stream are ordered and every kernel leaves them zero."""
+    if not _FUSED_FINISH:
+        return None, None
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream)
+    buf = _counters.get(key)
+    if buf is None or buf.numel() < n_out:
+        buf = torch.zeros(max(1024, n_out), device=dev, dtype=torch.int32)
+        _counters[key] = buf
+    return torch.empty(n_out, device=dev, dtype=torch.float64), buf
+
+
 def sum_partials(partials, n_per, n_out):
     out = torch.empty(n_out, device=partials.device, dtype=torch.float64)
     lib = _lib.load()
@@ -403,10 +423,13 @@ def blend_residual(mode, mask, a, b, x_cur, want_pred=True, want_res=True, want_
     part = torch.empty(N * nb, device=x.device, dtype=torch.float64) if want_sse else None
     lib = _lib.load()
     planes = 9 + (0 if mode == "half" else (2 if mode == "normw" else 1)) + 3 * int(want_pred) + 3 * int(want_res)
+    tot, cnt = _finish(x.device, N) if want_sse else (None, None)
+    p = lambda t: t.data_ptr() if t is not None else None
     _run("blend_residual_f32", planes * 4 * N * H * W, lambda: lib.b200vc_blend_residual_f32(
         _BLENDS[mode], mp, ap, abs_, bp, bbs, x.data_ptr(), pred.data_ptr() if want_pred else None,
-        res.data_ptr() if want_res else None, part.data_ptr() if want_sse else None, nb, N, H, W, _stream()))
-    sse = sum_partials(part, nb, N) if want_sse else None
+        res.data_ptr() if want_res else None, part.data_ptr() if want_sse else None, nb, p(tot), p(cnt), N, H, W,
+        _stream()))
+    sse = (tot if tot is not None else sum_partials(part, nb, N)) if want_sse else None
     return pred, res, sse
 
 
@@ -421,9 +444,11 @@ def sse_u8(a, b, h, w):
     nb = reduce_blocks(C * h * w)
     part = torch.empty(N * nb, device=a.device, dtype=torch.float64)
     lib = _lib.load()
+    tot, cnt = _finish(a.device, N)
+    p = lambda t: t.data_ptr() if t is not None else None
     _run("sse_u8_f32", 8 * N * C * h * w, lambda: lib.b200vc_sse_u8_f32(
-        a.data_ptr(), b.data_ptr(), part.data_ptr(), nb, N, C, H, W, h, w, _stream()))
-    return sum_partials(part, nb, N)
+        a.data_ptr(), b.data_ptr(), part.data_ptr(), nb, p(tot), p(cnt), N, C, H, W, h, w, _stream()))
+    return tot if tot is not None else sum_partials(part, nb, N)
 
 
 # --------------------------------------------------------------------------------------- GDN
@@ -509,11 +534,12 @@ def gauss_cond(y, scales, means, scale_bound=0.11, lik_bound=1e-9, inv_gain=None
     p = lambda t: t.data_ptr() if t is not None else None
     lib = _lib.load()
     words = 3 + int(want_y_hat) + int(want_lik) + 2 * int(want_symbols)
+    tot, cnt = _finish(dev, N) if want_bits else (None, None)
     _run("gauss_cond_f32", words * 4 * y.numel(), lambda: lib.b200vc_gauss_cond_f32(
         y.data_ptr(), sp, mp, sbs, p(inv_gain), p(y_hat), p(lik), p(sym), p(idx),
         p(scale_table) if want_symbols else None, scale_table.numel() if want_symbols else 0, float(scale_bound),
-        float(lik_bound), p(part), nb, N, C, H * W, _stream()))
-    bits = sum_partials(part, nb, N) if want_bits else None
+        float(lik_bound), p(part), nb, p(tot), p(cnt), N, C, H * W, _stream()), tag=f"{N}x{C}x{H}x{W}")
+    bits = (tot if tot is not None else sum_partials(part, nb, N)) if want_bits else None
     return {"y_hat": y_hat, "lik": lik, "bits": bits, "symbols": sym, "indexes": idx}
 
 
@@ -556,8 +582,9 @@ def entropy_bottleneck(z, packed, lik_bound=1e-9, gain=None, inv_gain=None, want
     p = lambda t: t.data_ptr() if t is not None else None
     lib = _lib.load()
     words = 1 + int(want_z_hat) + int(want_lik) + int(want_symbols)
+    tot, cnt = _finish(dev, N) if want_bits else (None, None)
     _run("entropy_bottleneck_f32", words * 4 * z.numel(), lambda: lib.b200vc_entropy_bottleneck_f32(
         z.data_ptr(), packed.data_ptr(), p(gain), p(inv_gain), p(z_hat), p(lik), p(sym), float(lik_bound), p(part),
-        nb, N, C, H * W, _stream()))
-    bits = sum_partials(part, nb, N) if want_bits else None
+        nb, p(tot), p(cnt), N, C, H * W, _stream()))
+    bits = (tot if tot is not None else sum_partials(part, nb, N)) if want_bits else None
     return {"z_hat": z_hat, "lik": lik, "bits": bits, "symbols": sym}

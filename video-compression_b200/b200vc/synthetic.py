@@ -114,3 +114,27 @@ def make_sequence(T, H=1080, W=1920, seed=1234, device="cpu", max_motion=8, nois
         win = canvas[:, dy:dy + H, dx:dx + W]
         frames[t] = (win + noise * torch.randn(win.shape, generator=g)).clamp_(0, 1)
     return frames.to(device)
+
+
+def make_frames(indices, H=1080, W=1920, seed=1234, device="cpu", max_motion=8, noise=0.01):
+    """Random-access variant of ``make_sequence`` for GOP-sharded runs: frame ``t`` depends on ``(seed, t)`` only
+    (its noise comes from its own generator), so every rank can build exactly the frames of its shard and any two
+    ranks agree bit for bit on a frame they both hold (the shared anchors).  The drifting canvas is the same
+    construction as ``make_sequence``'s."""
+    g = torch.Generator().manual_seed(seed)
+    margin = max_motion * 2 + 8
+    ch, cw = (H + 2 * margin + 31) // 32, (W + 2 * margin + 31) // 32
+    coarse = torch.rand(1, 3, ch + 1, cw + 1, generator=g)
+    canvas = F.interpolate(coarse, size=((ch + 1) * 32, (cw + 1) * 32), mode="bicubic", align_corners=False)
+    fine = torch.rand(1, 3, (ch + 1) * 4, (cw + 1) * 4, generator=g)
+    canvas = (0.8 * canvas + 0.2 * F.interpolate(fine, size=canvas.shape[-2:], mode="bilinear",
+                                                 align_corners=False)).clamp_(0, 1)[0]
+    indices = list(indices)
+    frames = torch.empty(len(indices), 3, H, W)
+    for k, t in enumerate(indices):
+        gt = torch.Generator().manual_seed(seed * 1000003 + 7919 * int(t) + 1)
+        dx = margin + int(round(max_motion * math.sin(0.37 * t)))
+        dy = margin + int(round(0.5 * max_motion * math.cos(0.23 * t)))
+        win = canvas[:, dy:dy + H, dx:dx + W]
+        frames[k] = (win + noise * torch.randn(win.shape, generator=gt)).clamp_(0, 1)
+    return frames.to(device)

@@ -30,7 +30,8 @@ template <int VEC>
 __global__ void __launch_bounds__(kBlendThreads)
 blend_kernel(int mode, const float* __restrict__ mask, const float* __restrict__ a, int64_t a_bs,
              const float* __restrict__ b, int64_t b_bs, const float* __restrict__ x,
-             float* __restrict__ pred, float* __restrict__ res, double* __restrict__ sse_partials, int64_t P) {
+             float* __restrict__ pred, float* __restrict__ res, double* __restrict__ sse_partials, int64_t P,
+             Finish fin) {
   const int n = blockIdx.y;
   const int mask_ch = (mode == B200VC_BLEND_NORMW) ? 2 : 1;
   const float* mp = mask ? mask + (int64_t)n * mask_ch * P : nullptr;
@@ -86,7 +87,7 @@ blend_kernel(int mode, const float* __restrict__ mask, const float* __restrict__
   }
   if (sse_partials) {
     const double tot = block_sum_to_f64<kBlendThreads>(sse);
-    if (threadIdx.x == 0) sse_partials[(int64_t)n * gridDim.x + blockIdx.x] = tot;
+    publish_partial<kBlendThreads>(tot, sse_partials + (int64_t)n * gridDim.x, blockIdx.x, gridDim.x, n, fin);
   }
 }
 
@@ -101,7 +102,7 @@ __device__ __forceinline__ float sq_u8_diff(float a, float b) {
 
 __global__ void __launch_bounds__(kBlendThreads)
 sse_u8_kernel(const float* __restrict__ a0, const float* __restrict__ b0, double* __restrict__ partials,
-              int planes, int H, int W, int h, int w) {
+              int planes, int H, int W, int h, int w, Finish fin) {
   // blockIdx.y = sample: per-sample sums, so one launch scores all frames of a hierarchy level
   const float* a = a0 + (int64_t)blockIdx.y * planes * H * W;
   const float* b = b0 + (int64_t)blockIdx.y * planes * H * W;
@@ -129,11 +130,11 @@ sse_u8_kernel(const float* __restrict__ a0, const float* __restrict__ b0, double
   double d = warp_sum(dacc);
   if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = d;
   __syncthreads();
+  double tot = 0.0;
   if (threadIdx.x == 0) {
-    double tot = 0.0;
     for (int i = 0; i < kBlendThreads / 32; ++i) tot += s_part[i];
-    partials[(int64_t)blockIdx.y * gridDim.x + blockIdx.x] = tot;
   }
+  publish_partial<kBlendThreads>(tot, partials + (int64_t)blockIdx.y * gridDim.x, blockIdx.x, gridDim.x, blockIdx.y, fin);
 }
 
 __global__ void sum_partials_kernel(const double* __restrict__ partials, int n_per, double* __restrict__ out) {
@@ -160,8 +161,9 @@ using namespace b200vc;
 
 extern "C" int b200vc_blend_residual_f32(int mode, const float* mask, const float* a, int64_t a_bs,
                                          const float* b, int64_t b_bs, const float* x_cur, float* pred,
-                                         float* res, double* sse_partials, int n_blocks, int N, int H, int W,
-                                         void* stream) {
+                                         float* res, double* sse_partials, int n_blocks, double* sse_totals,
+                                         int32_t* counters, int N, int H, int W, void* stream) {
+  B200VC_REQUIRE(!sse_totals || (sse_partials && counters), "blend_residual_f32: totals need partials and counters");
   B200VC_REQUIRE(a && b && x_cur, "blend_residual_f32: null pointer");
   B200VC_REQUIRE(mode >= 0 && mode <= 2, "blend_residual_f32: unknown mode %d", mode);
   B200VC_REQUIRE(mode == B200VC_BLEND_HALF || mask, "blend_residual_f32: mask required for mode %d", mode);
@@ -173,20 +175,22 @@ extern "C" int b200vc_blend_residual_f32(int mode, const float* mask, const floa
   cudaStream_t st = (cudaStream_t)stream;
   if (vec)
     blend_kernel<4><<<grid, kBlendThreads, 0, st>>>(mode, mask, a, a_bs, b, b_bs, x_cur, pred, res,
-                                                    sse_partials, P);
+                                                    sse_partials, P, Finish{sse_totals, counters});
   else
     blend_kernel<1><<<grid, kBlendThreads, 0, st>>>(mode, mask, a, a_bs, b, b_bs, x_cur, pred, res,
-                                                    sse_partials, P);
+                                                    sse_partials, P, Finish{sse_totals, counters});
   return check_launch("blend_residual_f32");
 }
 
-extern "C" int b200vc_sse_u8_f32(const float* a, const float* b, double* partials, int n_blocks, int N,
-                                 int C, int H, int W, int h, int w, void* stream) {
+extern "C" int b200vc_sse_u8_f32(const float* a, const float* b, double* partials, int n_blocks, double* totals,
+                                 int32_t* counters, int N, int C, int H, int W, int h, int w, void* stream) {
+  B200VC_REQUIRE(!totals || counters, "sse_u8_f32: totals need counters");
   B200VC_REQUIRE(a && b && partials, "sse_u8_f32: null pointer");
   B200VC_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && h > 0 && w > 0 && h <= H && w <= W && n_blocks > 0,
                  "sse_u8_f32: bad shape");
   B200VC_REQUIRE(N <= 65535, "sse_u8_f32: N too large");
-  sse_u8_kernel<<<dim3(n_blocks, N), kBlendThreads, 0, (cudaStream_t)stream>>>(a, b, partials, C, H, W, h, w);
+  sse_u8_kernel<<<dim3(n_blocks, N), kBlendThreads, 0, (cudaStream_t)stream>>>(a, b, partials, C, H, W, h, w,
+                                                                               Finish{totals, counters});
   return check_launch("sse_u8_f32");
 }
 

@@ -52,6 +52,50 @@ __device__ __forceinline__ double block_sum_to_f64(float v) {
   return tot;
 }
 
+// Optional fused finish of the per-CTA partials ("last CTA done"): every CTA publishes its fp64 partial, takes a
+// ticket on the sample's counter, and the CTA that draws the last ticket re-reads ALL partials of the sample in the
+// same strided order + tree as sum_partials_kernel (blend.cu) -- so the total is bit-identical to the two-launch
+// form, independent of which CTA finishes last -- writes totals[sample] and re-arms the counter (0).  Counters must
+// be zero on entry; the kernels leave them zero.  totals == nullptr keeps the two-launch form.
+struct Finish {
+  double* totals;
+  int32_t* counters;
+};
+
+// Must be called by every thread of the CTA; `tot` is read from thread 0 only.
+template <int kThreads>
+__device__ __forceinline__ void publish_partial(double tot, double* __restrict__ sample_partials, int idx,
+                                                int n_per, int sample, Finish f) {
+  static_assert(kThreads == 256, "must mirror sum_partials_kernel's 256-thread reduction order");
+  __shared__ int s_last;
+  if (threadIdx.x == 0) {
+    sample_partials[idx] = tot;
+    int last = 0;
+    if (f.totals != nullptr) {
+      __threadfence();  // the partial is visible device-wide before the ticket is
+      last = atomicAdd(f.counters + sample, 1) == n_per - 1;
+    }
+    s_last = last;
+  }
+  if (f.totals == nullptr) return;  // uniform
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double v = 0.0;
+  for (int k = threadIdx.x; k < n_per; k += kThreads) v += __ldcg(sample_partials + k);
+  __shared__ double s_fin[kThreads / 32];
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) s_fin[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < kThreads / 32; ++i) t += s_fin[i];
+    f.totals[sample] = t;
+    f.counters[sample] = 0;
+  }
+}
+
 // ATen CUDA sigmoid for float: 1 / (1 + exp(-x)).
 __device__ __forceinline__ float sigmoid_f(float x) { return __fdiv_rn(1.f, __fadd_rn(1.f, expf(-x))); }
 

@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(kWarpThreads)
 warp2_half_sse_kernel(const float* __restrict__ x1, const float* __restrict__ x2, const float* __restrict__ flow1,
                       const float* __restrict__ flow2, const float* __restrict__ x_cur,
                       const float* __restrict__ tab_x, const float* __restrict__ tab_y, float* __restrict__ pred_out,
-                      double* __restrict__ partials, WarpGeom g) {
+                      double* __restrict__ partials, WarpGeom g, Finish fin) {
   constexpr bool BORDER = (VARIANT != B200VC_WARP_FLEX);
   const int x = blockIdx.x * 32 + (threadIdx.x & 31);
   const int y = blockIdx.y * (kWarpThreads / 32) + (threadIdx.x >> 5);
@@ -228,8 +228,8 @@ warp2_half_sse_kernel(const float* __restrict__ x1, const float* __restrict__ x2
     }
   }
   const double tot = block_sum_to_f64<kWarpThreads>(sse);
-  if (threadIdx.x == 0)
-    partials[((int64_t)n * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = tot;
+  const int per = gridDim.x * gridDim.y;
+  publish_partial<kWarpThreads>(tot, partials + (int64_t)n * per, blockIdx.y * gridDim.x + blockIdx.x, per, n, fin);
 }
 
 // Single-reference search form (OJSP2025/video_model.py:621-666: x_hat = warp(ref_frame, est_mv) ; PSNR(x, x_hat)
@@ -239,7 +239,7 @@ template <int VARIANT>
 __global__ void __launch_bounds__(kWarpThreads)
 warp_sse_kernel(const float* __restrict__ img, const float* __restrict__ flow, const float* __restrict__ x_cur,
                 const float* __restrict__ tab_x, const float* __restrict__ tab_y, float* __restrict__ pred_out,
-                double* __restrict__ partials, WarpGeom g) {
+                double* __restrict__ partials, WarpGeom g, Finish fin) {
   constexpr bool BORDER = (VARIANT != B200VC_WARP_FLEX);
   const int x = blockIdx.x * 32 + (threadIdx.x & 31);
   const int y = blockIdx.y * (kWarpThreads / 32) + (threadIdx.x >> 5);
@@ -268,8 +268,8 @@ warp_sse_kernel(const float* __restrict__ img, const float* __restrict__ flow, c
     }
   }
   const double tot = block_sum_to_f64<kWarpThreads>(sse);
-  if (threadIdx.x == 0)
-    partials[((int64_t)n * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = tot;
+  const int per = gridDim.x * gridDim.y;
+  publish_partial<kWarpThreads>(tot, partials + (int64_t)n * per, blockIdx.y * gridDim.x + blockIdx.x, per, n, fin);
 }
 
 }  // namespace b200vc
@@ -388,7 +388,9 @@ extern "C" int b200vc_warp2_half_sse_blocks(int H, int W) {
 
 extern "C" int b200vc_warp2_half_sse_f32(const float* x1, const float* x2, const float* flow1, const float* flow2,
                                          const float* x_cur, const float* tab_x, const float* tab_y, float* pred,
-                                         double* partials, int N, int H, int W, int variant, void* stream) {
+                                         double* partials, double* totals, int32_t* counters, int N, int H, int W,
+                                         int variant, void* stream) {
+  B200VC_REQUIRE(!totals || counters, "warp2_half_sse_f32: totals need counters");
   B200VC_REQUIRE(x1 && x2 && flow1 && flow2 && x_cur && partials, "warp2_half_sse_f32: null pointer");
   B200VC_REQUIRE(N > 0 && N <= 65535 && H > 0 && W > 0, "warp2_half_sse_f32: bad shape");
   B200VC_REQUIRE(variant >= 0 && variant <= 2, "warp2_half_sse_f32: unknown variant %d", variant);
@@ -399,17 +401,18 @@ extern "C" int b200vc_warp2_half_sse_f32(const float* x1, const float* x2, const
   dim3 grid((W + 31) / 32, (H + rows - 1) / rows, N);
   cudaStream_t st = (cudaStream_t)stream;
   if (variant == B200VC_WARP_LHBDC)
-    warp2_half_sse_kernel<0><<<grid, kWarpThreads, 0, st>>>(x1, x2, flow1, flow2, x_cur, tab_x, tab_y, pred, partials, g);
+    warp2_half_sse_kernel<0><<<grid, kWarpThreads, 0, st>>>(x1, x2, flow1, flow2, x_cur, tab_x, tab_y, pred, partials, g, Finish{totals, counters});
   else if (variant == B200VC_WARP_FLEX)
-    warp2_half_sse_kernel<1><<<grid, kWarpThreads, 0, st>>>(x1, x2, flow1, flow2, x_cur, tab_x, tab_y, pred, partials, g);
+    warp2_half_sse_kernel<1><<<grid, kWarpThreads, 0, st>>>(x1, x2, flow1, flow2, x_cur, tab_x, tab_y, pred, partials, g, Finish{totals, counters});
   else
-    warp2_half_sse_kernel<2><<<grid, kWarpThreads, 0, st>>>(x1, x2, flow1, flow2, x_cur, tab_x, tab_y, pred, partials, g);
+    warp2_half_sse_kernel<2><<<grid, kWarpThreads, 0, st>>>(x1, x2, flow1, flow2, x_cur, tab_x, tab_y, pred, partials, g, Finish{totals, counters});
   return check_launch("warp2_half_sse_f32");
 }
 
 extern "C" int b200vc_warp_sse_f32(const float* img, const float* flow, const float* x_cur, const float* tab_x,
-                                   const float* tab_y, float* pred, double* partials, int N, int H, int W,
-                                   int variant, void* stream) {
+                                   const float* tab_y, float* pred, double* partials, double* totals,
+                                   int32_t* counters, int N, int H, int W, int variant, void* stream) {
+  B200VC_REQUIRE(!totals || counters, "warp_sse_f32: totals need counters");
   B200VC_REQUIRE(img && flow && x_cur && partials, "warp_sse_f32: null pointer");
   B200VC_REQUIRE(N > 0 && N <= 65535 && H > 0 && W > 0, "warp_sse_f32: bad shape");
   B200VC_REQUIRE(variant >= 0 && variant <= 2, "warp_sse_f32: unknown variant %d", variant);
@@ -420,10 +423,10 @@ extern "C" int b200vc_warp_sse_f32(const float* img, const float* flow, const fl
   dim3 grid((W + 31) / 32, (H + rows - 1) / rows, N);
   cudaStream_t st = (cudaStream_t)stream;
   if (variant == B200VC_WARP_LHBDC)
-    warp_sse_kernel<0><<<grid, kWarpThreads, 0, st>>>(img, flow, x_cur, tab_x, tab_y, pred, partials, g);
+    warp_sse_kernel<0><<<grid, kWarpThreads, 0, st>>>(img, flow, x_cur, tab_x, tab_y, pred, partials, g, Finish{totals, counters});
   else if (variant == B200VC_WARP_FLEX)
-    warp_sse_kernel<1><<<grid, kWarpThreads, 0, st>>>(img, flow, x_cur, tab_x, tab_y, pred, partials, g);
+    warp_sse_kernel<1><<<grid, kWarpThreads, 0, st>>>(img, flow, x_cur, tab_x, tab_y, pred, partials, g, Finish{totals, counters});
   else
-    warp_sse_kernel<2><<<grid, kWarpThreads, 0, st>>>(img, flow, x_cur, tab_x, tab_y, pred, partials, g);
+    warp_sse_kernel<2><<<grid, kWarpThreads, 0, st>>>(img, flow, x_cur, tab_x, tab_y, pred, partials, g, Finish{totals, counters});
   return check_launch("warp_sse_f32");
 }
