@@ -382,3 +382,74 @@ class MeanScaleHyperprior(ScaleHyperprior):
         if scale_table is None:
             scale_table = get_scale_table()
         return self.gaussian_conditional.update_scale_table(scale_table, force=force)
+
+
+class MaskedConv2d(nn.Conv2d):
+    """compressai.layers.MaskedConv2d (PixelCNN-style causal mask; type 'A' hides the centre too).  The ICIP models
+    inherit one as ``context_prediction`` from the joint-autoregressive container and never call it."""
+
+    def __init__(self, *args, mask_type="A", **kwargs):
+        super().__init__(*args, **kwargs)
+        if mask_type not in ("A", "B"):
+            raise ValueError(f'Invalid "mask_type" value "{mask_type}"')
+        self.register_buffer("mask", torch.ones_like(self.weight.data))
+        _, _, h, w = self.mask.size()
+        self.mask[:, :, h // 2, w // 2 + (mask_type == "B"):] = 0
+        self.mask[:, :, h // 2 + 1:] = 0
+
+    def forward(self, x):
+        self.weight.data *= self.mask
+        return super().forward(x)
+
+
+class JointAutoregressiveHierarchicalPriors(MeanScaleHyperprior):
+    """compressai.models.JointAutoregressiveHierarchicalPriors (Minnen 2018), the base class of the ICIP codecs'
+    ``Offset_ELIC`` / ``Res_ELIC`` / ``ELIC`` (ICIP2024/src/model/compression_bottlenecks.py:72, :313).  Those
+    subclasses replace ``h_a``, ``h_s`` and ``entropy_parameters`` and never call ``g_a``, ``g_s`` or
+    ``context_prediction`` -- but the members exist (state-dict keys of the reference checkpoints), so they are
+    built here as CompressAI builds them."""
+
+    def __init__(self, N=192, M=192, **kwargs):
+        super().__init__(N=N, M=M, **kwargs)
+        self.g_a = nn.Sequential(_conv5(3, N), GDN(N), _conv5(N, N), GDN(N), _conv5(N, N), GDN(N), _conv5(N, M))
+        self.g_s = nn.Sequential(
+            _deconv5(M, N), GDN(N, inverse=True), _deconv5(N, N), GDN(N, inverse=True),
+            _deconv5(N, N), GDN(N, inverse=True), _deconv5(N, 3),
+        )
+        self.h_a = nn.Sequential(
+            nn.Conv2d(M, N, 3, 1, 1), nn.LeakyReLU(inplace=True), _conv5(N, N), nn.LeakyReLU(inplace=True),
+            _conv5(N, N),
+        )
+        self.h_s = nn.Sequential(
+            _deconv5(N, M), nn.LeakyReLU(inplace=True), _deconv5(M, M * 3 // 2), nn.LeakyReLU(inplace=True),
+            nn.Conv2d(M * 3 // 2, M * 2, 3, 1, 1),
+        )
+        self.entropy_parameters = nn.Sequential(
+            nn.Conv2d(M * 12 // 3, M * 10 // 3, 1), nn.LeakyReLU(inplace=True),
+            nn.Conv2d(M * 10 // 3, M * 8 // 3, 1), nn.LeakyReLU(inplace=True),
+            nn.Conv2d(M * 8 // 3, M * 6 // 3, 1),
+        )
+        self.context_prediction = MaskedConv2d(M, 2 * M, kernel_size=5, padding=2, stride=1)
+        self.gaussian_conditional = GaussianConditional(None)
+        self.N = int(N)
+        self.M = int(M)
+
+    def forward(self, x):
+        y = self.g_a(x)
+        z = self.h_a(y)
+        z_hat, z_likelihoods = self.entropy_bottleneck(z)
+        params = self.h_s(z_hat)
+        y_hat = self.gaussian_conditional.quantize(y, "noise" if self.training else "dequantize")
+        ctx_params = self.context_prediction(y_hat)
+        gaussian_params = self.entropy_parameters(torch.cat((params, ctx_params), dim=1))
+        scales_hat, means_hat = gaussian_params.chunk(2, 1)
+        _, y_likelihoods = self.gaussian_conditional(y, scales_hat, means=means_hat)
+        x_hat = self.g_s(y_hat)
+        return {"x_hat": x_hat, "likelihoods": {"y": y_likelihoods, "z": z_likelihoods}}
+
+
+class Cheng2020Anchor(JointAutoregressiveHierarchicalPriors):
+    """Imported (never instantiated) at ICIP2024/src/model/compression_bottlenecks.py:7."""
+
+    def __init__(self, *args, **kwargs):
+        raise NotImplementedError("Cheng2020Anchor is imported but never instantiated by the reference")

@@ -30,6 +30,8 @@ def install():
         MeanScaleHyperprior=cai.MeanScaleHyperprior,
         ScaleHyperprior=cai.ScaleHyperprior,
         CompressionModel=cai.CompressionModel,
+        JointAutoregressiveHierarchicalPriors=cai.JointAutoregressiveHierarchicalPriors,
+        Cheng2020Anchor=cai.Cheng2020Anchor,
     )
     models.__path__ = []
     mutils = sub("models.utils", conv=cai._conv5, deconv=cai._deconv5)
@@ -43,6 +45,7 @@ def install():
     sub(
         "layers",
         GDN=cai.GDN,
+        MaskedConv2d=cai.MaskedConv2d,
         AttentionBlock=cai.AttentionBlock,
         ResidualBlock=cai.ResidualBlock,
         ResidualBlockUpsample=cai.ResidualBlockUpsample,
@@ -52,6 +55,12 @@ def install():
         subpel_conv3x3=cai.subpel_conv3x3,
     )
     sub("ops", LowerBound=cai.LowerBound, NonNegativeParametrizer=cai.NonNegativeParametrizer)
+
+    class _NoCoder:  # compressai.ans: the C++ rANS coder is imported by the ICIP model files, never built offline
+        def __init__(self, *a, **k):
+            raise NotImplementedError("compressai.ans is not available offline (oracle shim)")
+
+    sub("ans", BufferedRansEncoder=_NoCoder, RansDecoder=_NoCoder)
     sys.modules["compressai"] = root
     return root
 

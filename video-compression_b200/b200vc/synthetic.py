@@ -138,3 +138,40 @@ def make_frames(indices, H=1080, W=1920, seed=1234, device="cpu", max_motion=8, 
         win = canvas[:, dy:dy + H, dx:dx + W]
         frames[k] = (win + noise * torch.randn(win.shape, generator=gt)).clamp_(0, 1)
     return frames.to(device)
+
+
+@torch.no_grad()
+def calibrate_flowguided_(model, seed=0):
+    """Same idea for the ICIP2024 ``FlowGuidedB`` tree (reference attribute names: ICIP2024/src/model/m.py:31-49):
+    flows of a few pixels at the pooled resolution, latents over several bins through the gain tables (distinct per
+    rate level so that level interpolation matters), predicted scales over the table, perturbed factorised priors."""
+    g = torch.Generator().manual_seed(seed)
+    randn = lambda *s: torch.randn(*s, generator=g)
+    rand = lambda *s: torch.rand(*s, generator=g)
+
+    def put(p, value):
+        p.copy_(value.to(device=p.device, dtype=p.dtype))
+
+    last = model.flow_estimator.up3[-1][0]
+    last.weight.mul_(12.0)
+    last.bias.mul_(12.0)
+    for comp, base in ((model.offset_compressor, 6.0), (model.residual_compressor, 10.0)):
+        L, M = comp.Gain.shape
+        lvl = torch.linspace(0.6, 1.6, L).view(L, 1)
+        gain = base * lvl * (1.0 + 0.1 * randn(L, M))
+        put(comp.Gain, gain)
+        put(comp.InverseGain, (1.0 + 0.05 * randn(L, M)) / gain)
+        hgain = 3.0 * lvl * (1.0 + 0.1 * randn(L, comp.HyperGain.shape[1]))
+        put(comp.HyperGain, hgain)
+        put(comp.InverseHyperGain, (1.0 + 0.05 * randn(L, comp.HyperGain.shape[1])) / hgain)
+        for ep in comp.entropy_parameters:
+            c = ep[-1].bias.shape[0] // 2
+            put(ep[-1].bias[:c], torch.exp(math.log(0.05) + rand(c) * (math.log(20.0) - math.log(0.05))))
+        eb = comp.entropy_bottleneck
+        for i in range(4):
+            f = getattr(eb, f"_factor{i}")
+            put(f, 0.3 * randn(*f.shape))
+        q = eb.quantiles.cpu().clone()
+        q[:, 0, 1] = 0.5 * randn(q.shape[0])
+        put(eb.quantiles, q)
+    return model
