@@ -27,6 +27,9 @@ int launch_warp2_tma(const float* xb, const float* xa, const float* flow_hat, co
 int launch_warp2_v2(const float* xb, const float* xa, const float* flow_hat, const float* flow_ab,
                     const float* flow_ba, const float* tab_x, const float* tab_y, float* out, float* flows_out, int N,
                     int H, int W, int h4, int w4, const WarpGeom& g, cudaStream_t st);  // warp2.cu
+int launch_warp2_staged(const float* xb, const float* xa, const float* flow_hat, const float* flow_ab,
+                        const float* flow_ba, const float* tab_x, const float* tab_y, float* out, float* flows_out,
+                        int N, int H, int W, int h4, int w4, const WarpGeom& g, cudaStream_t st);  // warp2.cu
 int launch_warp_tma(const float* img, int64_t img_bs, const float* flow, const float* tab_x, const float* tab_y,
                     float* out, int64_t out_bs, int N, int C, int H, int W, const WarpGeom& g, cudaStream_t st);  // warp_tma.cu
 
@@ -368,6 +371,9 @@ extern "C" int b200vc_warp2_lhbdc_f32(const float* x_before, const float* x_afte
     const int rc = launch_warp2_tma(x_before, x_after, flow_hat, flow_ab, flow_ba, tab_x, tab_y, out, flows_out, N, H, W,
                                     h4, w4, g, (cudaStream_t)stream);
     if (rc != B200VC_EUNSUPPORTED) return rc;
+    const int rc3 = launch_warp2_staged(x_before, x_after, flow_hat, flow_ab, flow_ba, tab_x, tab_y, out, flows_out, N, H,
+                                        W, h4, w4, g, (cudaStream_t)stream);
+    if (rc3 != B200VC_EUNSUPPORTED) return rc3;
     const int rc2 = launch_warp2_v2(x_before, x_after, flow_hat, flow_ab, flow_ba, tab_x, tab_y, out, flows_out, N, H, W,
                                     h4, w4, g, (cudaStream_t)stream);
     if (rc2 != B200VC_EUNSUPPORTED) return rc2;

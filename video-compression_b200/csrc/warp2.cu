@@ -15,7 +15,10 @@
 //   * tap offsets are 32-bit against warp-uniform plane bases; the border variant needs no int-range guard (the
 //     clip maps NaN to 0 and everything else into [0, size-1]); `(float)(x0 + 1)` is `floor(ix) + 1`.
 // Algorithmic bytes: 2 x 3 planes read + 6 planes written + quarter-resolution flows = 50 B/px.
+#include <cuda.h>
 #include <stdlib.h>
+
+#include <mutex>
 
 #include "common.cuh"
 #include "warp_common.cuh"
@@ -41,6 +44,8 @@ __device__ __forceinline__ Cell cell_of(int dst) {
   r.l0 = __fsub_rn(1.f, r.l1);
   return r;
 }
+
+__device__ __forceinline__ float ldg_tap(const float* p) { return __ldg(p); }
 
 template <bool FLOWS>
 __global__ void __launch_bounds__(kThreads)
@@ -157,18 +162,30 @@ warp2_kernel(const float* __restrict__ xb, const float* __restrict__ xa, const f
       for (int c = 0; c < 3; ++c) {
         const float* rc0 = pin[dir][c] + q0;
         const float* rc1 = pin[dir][c] + q1;
-        t[dir][c][0] = __ldg(rc0);
-        t[dir][c][1] = __ldg(rc0 + 1);
-        t[dir][c][2] = __ldg(rc1);
-        t[dir][c][3] = __ldg(rc1 + 1);
+        t[dir][c][0] = ldg_tap(rc0);
+        t[dir][c][1] = ldg_tap(rc0 + 1);
+        t[dir][c][2] = ldg_tap(rc1);
+        t[dir][c][3] = ldg_tap(rc1 + 1);
       }
     }
+    // Scheduling fence that survives ptxas: the accumulators start from a +0.0f that is *data-dependent on every
+    // gather of the pixel* (OR of their bits AND a kernel argument that is 0 in this instantiation), so no FMA chain can be placed between
+    // the loads -- the SM issues in order, and a consumer scheduled early stalls the issue of the remaining gathers
+    // on its scoreboard (first build: 4-6 of 24 taps in flight, 80 % long-scoreboard stalls, 0.37 IPC).
+    int any = 0;
+#pragma unroll
+    for (int dir = 0; dir < 2; ++dir)
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        any |= __float_as_int(t[dir][c][0]) | __float_as_int(t[dir][c][1]) | __float_as_int(t[dir][c][2]) |
+               __float_as_int(t[dir][c][3]);
+    const float zero = __int_as_float(any & g.arith);
 #pragma unroll
     for (int dir = 0; dir < 2; ++dir) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         // ATen: out_acc = 0; out_acc += v * w per tap in nw, ne, sw, se order (FMA-contracted)
-        float acc = __fmaf_rn(t[dir][c][0], w[dir][0], 0.f);
+        float acc = __fmaf_rn(t[dir][c][0], w[dir][0], zero);
         acc = __fmaf_rn(t[dir][c][1], w[dir][1], acc);
         acc = __fmaf_rn(t[dir][c][2], w[dir][2], acc);
         acc = __fmaf_rn(t[dir][c][3], w[dir][3], acc);
@@ -198,6 +215,261 @@ int launch_warp2_v2(const float* xb, const float* xa, const float* flow_hat, con
     warp2_kernel<false><<<grid, kThreads, 0, st>>>(xb, xa, flow_hat, flow_ab, flow_ba, tab_x, tab_y, out, flows_out,
                                                     h4, w4, g);
   return check_launch("warp2_lhbdc_f32(v2)");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K-WARP2, TMA-staged form (the default for frames >= 128 x 128): what the gather form above cannot fix is its L1
+// traffic -- a warp's gather of 32 neighbouring, unaligned pixels is two L1 wavefronts, 24 of them per pixel, and
+// ncu shows both generations of the gather kernel converging on the same ~36 us per 1088 x 1920 frame with the L1
+// data pipe as the busiest unit.  Here the reference-frame tile around a CTA's flow footprint arrives by ONE 3-D TMA
+// box copy per direction (no LSU traffic, zero fill outside the frame = ATen's skipped taps), and every tap is a
+// conflict-free shared-memory read at an immediate offset from one address per pixel.  The older staged kernel
+// (warp_tma.cu: warp2_tma_kernel, kept behind B200VC_WARP2_TMA=1) has this structure but ~470 instructions per pixel
+// (issue-bound, ncu IPC 2.7); this one keeps the lean chains of the gather form.
+namespace w3 {
+
+constexpr int kTW = 64, kTH = 32, kThreads = 256, kPX = 8;     // tile; thread = 8 pixels of one column, rows ty + 4k
+constexpr int kBW = 96, kBH = 48;                               // staged box: tile + 16 / 8 pixels of flow spread
+constexpr int kBoxBytes = 3 * kBW * kBH * 4;
+constexpr int kSmemBytes = kBoxBytes + 128;
+constexpr int kQC = kTW / 4 + 2, kQR = kTH / 4 + 1;             // quarter-resolution cells a tile can start in
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <bool FLOWS>
+__global__ void __launch_bounds__(kThreads, 3)
+warp2_staged_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_a,
+                    const float* __restrict__ xb, const float* __restrict__ xa, const float* __restrict__ flow_hat,
+                    const float* __restrict__ flow_ab, const float* __restrict__ flow_ba,
+                    const float* __restrict__ tab_x, const float* __restrict__ tab_y, float* __restrict__ out,
+                    float* __restrict__ flows_out, int h4, int w4, WarpGeom g) {
+  extern __shared__ uint8_t smem_raw[];
+  float* tile = reinterpret_cast<float*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));  // [3][kBH][kBW]
+  __shared__ float4 s_c[4][kQR][kQC];
+  __shared__ int s_red[kThreads / 32][4];
+  __shared__ int s_box[3];
+  __shared__ __align__(8) uint64_t s_bar;
+
+  const int tid = threadIdx.x;
+  const int tx = tid & (kTW - 1), ty = tid >> 6;
+  const int bx = blockIdx.x * kTW, by = blockIdx.y * kTH;
+  const int n = blockIdx.z;
+  const int HW = g.H * g.W;
+  const int hh = g.H >> 2, ww = g.W >> 2;
+  const bool xin = bx + tx < g.W;
+  const int x = xin ? bx + tx : g.W - 1;
+
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  const int qx0 = max((bx >> 2) - 1, 0), qy0 = max((by >> 2) - 1, 0);
+  {
+    const int q = h4 * w4;
+    for (int e = tid; e < 4 * kQR * kQC; e += kThreads) {
+      const int ch = e / (kQR * kQC), r = (e / kQC) % kQR, c = e % kQC;
+      const int y0 = min(qy0 + r, hh - 1) * w4, y1 = min(qy0 + r + 1, hh - 1) * w4;
+      const int x0 = min(qx0 + c, ww - 1), x1 = min(qx0 + c + 1, ww - 1);
+      const float* pri = (ch < 2 ? flow_ab : flow_ba) + ((int64_t)n * 2 + (ch & 1)) * q;
+      const float* hat = flow_hat + ((int64_t)n * 4 + ch) * q;
+      float4 v;
+      v.x = __fadd_rn(__ldg(hat + y0 + x0), __ldg(pri + y0 + x0));
+      v.y = __fadd_rn(__ldg(hat + y0 + x1), __ldg(pri + y0 + x1));
+      v.z = __fadd_rn(__ldg(hat + y1 + x0), __ldg(pri + y1 + x0));
+      v.w = __fadd_rn(__ldg(hat + y1 + x1), __ldg(pri + y1 + x1));
+      s_c[ch][r][c] = v;
+    }
+  }
+  __syncthreads();
+
+  const w2::Cell cx = w2::cell_of(x);
+  const int rc = cx.i0 - qx0;
+  const float txv = __ldg(tab_x + x);
+  const float wmax = (float)(g.W - 1), hmax = (float)(g.H - 1);
+  const float fW = (float)g.W, fH = (float)g.H;
+  // row state of the thread's 8 pixels: rows by + ty + 4k share their upsample weights from k = 1 on (same y mod 4,
+  // no top-border clamp), and their source cell advances by one per k
+  const int yk0 = min(by + ty, g.H - 1), yk1 = min(by + ty + 4, g.H - 1);
+  const w2::Cell cy0 = w2::cell_of(yk0), cy1 = w2::cell_of(yk1);
+  const int o0 = (by + ty) * g.W + x;
+
+  uint32_t phase = 0;  // parity of the next box copy (a direction that falls back to gathers does not use the barrier)
+#pragma unroll 1
+  for (int dir = 0; dir < 2; ++dir) {
+    float ix[kPX], iy[kPX];
+    int mnx = 0x7fffffff, mxx = -0x7fffffff - 1, mny = 0x7fffffff, mxy = -0x7fffffff - 1;
+#pragma unroll
+    for (int k = 0; k < kPX; ++k) {
+      const int yr = by + ty + 4 * k;
+      const int y = min(yr, g.H - 1);
+      const float l0y = k == 0 ? cy0.l0 : cy1.l0, l1y = k == 0 ? cy0.l1 : cy1.l1;
+      // rows past the frame (partial bottom tile) repeat the last row's cell; their results are never stored
+      const int ry = min((k == 0 ? cy0.i0 : cy1.i0 + (k - 1)), hh - 1) - qy0;
+      const float4 cu = s_c[2 * dir][min(ry, kQR - 1)][rc], cv = s_c[2 * dir + 1][min(ry, kQR - 1)][rc];
+      const float u = __fmaf_rn(l0y, __fmaf_rn(cx.l0, cu.x, __fmul_rn(cx.l1, cu.y)),
+                                __fmul_rn(l1y, __fmaf_rn(cx.l0, cu.z, __fmul_rn(cx.l1, cu.w))));
+      const float v = __fmaf_rn(l0y, __fmaf_rn(cx.l0, cv.x, __fmul_rn(cx.l1, cv.y)),
+                                __fmul_rn(l1y, __fmaf_rn(cx.l0, cv.z, __fmul_rn(cx.l1, cv.w))));
+      if (FLOWS && xin && yr < g.H) {
+        float* fo = flows_out + ((int64_t)n * 4 + dir * 2) * HW + o0 + 4 * k * g.W;
+        __stcg(fo, u);
+        __stcg(fo + HW, v);
+      }
+      const float gx = __fadd_rn(txv, __fmul_rn(u, g.inv_x));
+      const float gy = __fadd_rn(__ldg(tab_y + y), __fmul_rn(v, g.inv_y));
+      const float px = __fmul_rn(__fmaf_rn(__fadd_rn(gx, 1.f), fW, -1.f), 0.5f);
+      const float py = __fmul_rn(__fmaf_rn(__fadd_rn(gy, 1.f), fH, -1.f), 0.5f);
+      ix[k] = fminf(wmax, fmaxf(px, 0.f));
+      iy[k] = fminf(hmax, fmaxf(py, 0.f));
+      const int x0 = (int)ix[k], y0 = (int)iy[k];      // >= 0 after the clip: truncation == floor
+      mnx = min(mnx, x0); mxx = max(mxx, x0);
+      mny = min(mny, y0); mxy = max(mxy, y0);
+    }
+    // ---- block-wide bounding box of the footprint (taps x0..x0+1, y0..y0+1)
+    mnx = __reduce_min_sync(0xffffffffu, mnx); mxx = __reduce_max_sync(0xffffffffu, mxx);
+    mny = __reduce_min_sync(0xffffffffu, mny); mxy = __reduce_max_sync(0xffffffffu, mxy);
+    if ((tid & 31) == 0) {
+      s_red[tid >> 5][0] = mnx; s_red[tid >> 5][1] = mxx; s_red[tid >> 5][2] = mny; s_red[tid >> 5][3] = mxy;
+    }
+    __syncthreads();  // also: every thread has finished reading the box of the previous direction
+    if (tid == 0) {
+      int a = s_red[0][0], b = s_red[0][1], c = s_red[0][2], d = s_red[0][3];
+#pragma unroll
+      for (int w = 1; w < kThreads / 32; ++w) {
+        a = min(a, s_red[w][0]); b = max(b, s_red[w][1]); c = min(c, s_red[w][2]); d = max(d, s_red[w][3]);
+      }
+      a &= ~3;  // TMA: the innermost start coordinate must sit on a 16-byte boundary (unaligned starts fault)
+      const bool fits = (b + 2 - a <= kBW) && (d + 2 - c <= kBH);
+      s_box[0] = a; s_box[1] = c; s_box[2] = fits ? 1 : 0;
+      if (fits) {
+        const uint32_t bar = smem_u32(&s_bar);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kBoxBytes) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+            ::"r"(smem_u32(tile)), "l"(reinterpret_cast<uint64_t>(dir == 0 ? &map_b : &map_a)), "r"(bar), "r"(a),
+              "r"(c), "r"(n * 3)
+            : "memory");
+      }
+    }
+    __syncthreads();
+    const int bx0 = s_box[0], by0 = s_box[1];
+    const bool staged = s_box[2] != 0;
+    float* op = out + ((int64_t)n * 6 + dir * 3) * HW + o0;
+    if (staged) {
+      const uint32_t bar = smem_u32(&s_bar);
+      uint32_t done = 0;
+      for (uint32_t spins = 0; !done; ++spins) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(phase) : "memory");
+        if (spins > (1u << 26)) __trap();
+      }
+      phase ^= 1u;
+      const float* tb = tile - by0 * kBW - bx0;
+#pragma unroll
+      for (int k = 0; k < kPX; ++k) {
+        const int x0 = (int)ix[k], y0 = (int)iy[k];
+        const float fx = (float)x0, fy = (float)y0;
+        const float dx1 = __fsub_rn(__fadd_rn(fx, 1.f), ix[k]), dx0 = __fsub_rn(ix[k], fx);
+        const float dy1 = __fsub_rn(__fadd_rn(fy, 1.f), iy[k]), dy0 = __fsub_rn(iy[k], fy);
+        const float w00 = __fmul_rn(dx1, dy1), w01 = __fmul_rn(dx0, dy1);
+        const float w10 = __fmul_rn(dx1, dy0), w11 = __fmul_rn(dx0, dy0);
+        // taps outside the frame read TMA's zero fill: v * w == 0 exactly, the same as ATen skipping the tap
+        const float* t = tb + y0 * kBW + x0;
+        float r[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float acc = __fmaf_rn(t[c * (kBH * kBW)], w00, 0.f);
+          acc = __fmaf_rn(t[c * (kBH * kBW) + 1], w01, acc);
+          acc = __fmaf_rn(t[c * (kBH * kBW) + kBW], w10, acc);
+          r[c] = __fmaf_rn(t[c * (kBH * kBW) + kBW + 1], w11, acc);
+        }
+        if (xin && by + ty + 4 * k < g.H) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) __stcg(op + c * HW + 4 * k * g.W, r[c]);
+        }
+      }
+    } else {
+      // footprint wider than the box (divergent flow): direct gathers, same arithmetic
+      const float* ip = (dir == 0 ? xb : xa) + (int64_t)n * 3 * HW;
+#pragma unroll
+      for (int k = 0; k < kPX; ++k) {
+        const Taps t = make_taps<true>(ix[k], iy[k], g.H, g.W);
+        if (xin && by + ty + 4 * k < g.H) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) __stcg(op + c * HW + 4 * k * g.W, sample<true>(ip + (int64_t)c * HW, t));
+        }
+      }
+    }
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      return reinterpret_cast<EncodeTiledFn>(p);
+    return nullptr;
+  }();
+  return fn;
+}
+
+static bool make_img_map(CUtensorMap* map, const float* img, int N, int H, int W) {
+  EncodeTiledFn enc = encode_fn();
+  if (enc == nullptr) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N * 3};
+  cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4};
+  cuuint32_t box[3] = {kBW, kBH, 3};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(img), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace w3
+
+int launch_warp2_staged(const float* xb, const float* xa, const float* flow_hat, const float* flow_ab,
+                        const float* flow_ba, const float* tab_x, const float* tab_y, float* out, float* flows_out,
+                        int N, int H, int W, int h4, int w4, const WarpGeom& g, cudaStream_t st) {
+  using namespace w3;
+  static const int enabled = []() {
+    const char* e = getenv("B200VC_WARP2_STAGED");
+    return e ? atoi(e) : 1;
+  }();
+  if (!enabled || W % 4 != 0 || H < 2 || W < 2 || (int64_t)H * W < 128 * 128 || (int64_t)N * 3 >= (1 << 30) ||
+      ((reinterpret_cast<uintptr_t>(xb) | reinterpret_cast<uintptr_t>(xa)) & 15u) != 0)
+    return B200VC_EUNSUPPORTED;
+  CUtensorMap map_b, map_a;
+  if (!make_img_map(&map_b, xb, N, H, W) || !make_img_map(&map_a, xa, N, H, W)) return B200VC_EUNSUPPORTED;
+  static std::once_flag once[64];
+  static bool ok[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return B200VC_EUNSUPPORTED;
+  std::call_once(once[dev], [&]() {
+    ok[dev] = cudaFuncSetAttribute(warp2_staged_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   kSmemBytes) == cudaSuccess &&
+              cudaFuncSetAttribute(warp2_staged_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   kSmemBytes) == cudaSuccess;
+    if (!ok[dev]) (void)cudaGetLastError();
+  });
+  if (!ok[dev]) return B200VC_EUNSUPPORTED;
+  dim3 grid((W + kTW - 1) / kTW, (H + kTH - 1) / kTH, N);
+  if (flows_out != nullptr)
+    warp2_staged_kernel<true><<<grid, kThreads, kSmemBytes, st>>>(map_b, map_a, xb, xa, flow_hat, flow_ab, flow_ba,
+                                                                  tab_x, tab_y, out, flows_out, h4, w4, g);
+  else
+    warp2_staged_kernel<false><<<grid, kThreads, kSmemBytes, st>>>(map_b, map_a, xb, xa, flow_hat, flow_ab, flow_ba,
+                                                                   tab_x, tab_y, out, flows_out, h4, w4, g);
+  return check_launch("warp2_lhbdc_f32(staged)");
 }
 
 }  // namespace b200vc

@@ -297,6 +297,7 @@ warp2_tma_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
   const float txv = __ldg(tab_x + xc);
   float* op = out + (int64_t)n * 6 * HW;
 
+  uint32_t phase = 0;
 #pragma unroll 1
   for (int dir = 0; dir < 2; ++dir) {
     float ix[kPX], iy[kPX];
@@ -359,9 +360,10 @@ warp2_tma_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(bar), "r"(dir) : "memory");
+            : "=r"(done) : "r"(bar), "r"(phase) : "memory");
         if (spins > (1u << 26)) __trap();
       }
+      phase ^= 1u;  // a direction that fell back to gathers never used the barrier: parity follows the copies, not `dir`
     }
     const float* ip = (dir == 0 ? xb : xa) + (int64_t)n * 3 * HW;
 #pragma unroll
