@@ -191,3 +191,21 @@ def test_elic_group_layout_is_validated_before_any_kernel_runs():
             icip.elic_context_likelihoods(torch.zeros(1, M, 2, 2), None, None, None, None, None)
     with pytest.raises(ValueError):
         icip.elic_context_likelihoods(torch.zeros(1, 64, 2, 2), None, None, None, None, None, group_sizes=(6, 6))
+
+
+def test_flowguided_mirror_has_the_reference_checkpoint_layout():
+    """b200vc.flowguided.FlowGuidedB: same state-dict keys and shapes as the oracle restatement, which
+    oracle/make_golden_flowguided.py pins key for key to the reference's ICIP2024/src/model/m.py."""
+    import torch
+    from b200vc import flowguided
+    from oracle import flowguided as o_fg
+    torch.manual_seed(0)
+    ref, mir = o_fg.FlowGuidedB().state_dict(), flowguided.FlowGuidedB().state_dict()
+    assert set(ref) == set(mir)
+    assert all(ref[k].shape == mir[k].shape for k in ref)
+    for n in (2, 17, 40, 300, 600):
+        assert flowguided.get_order_typ_list(16, n) == o_fg.get_order_typ_list(16, n)
+    for order, buf in ((8, [0, 16]), (4, [0, 16, 8]), (12, [0, 16, 8, 4]), (1, [0]), (598, [599, 595, 593, 597, 594, 596])):
+        assert flowguided.select_references(order, buf) == o_fg.select_references(order, buf)
+    assert flowguided.get_scales(4, 0, 8) == o_fg.get_scales(4, 0, 8) == (0.5, 0.5)
+    assert flowguided.get_scales(3, 3, 3) == (0, 0)

@@ -7,7 +7,8 @@ Layout
   ops.py                tensor-level wrappers (one per reference call chain)
   modules.py            CompressAI-interface mirror (GDN, EntropyBottleneck, GaussianConditional, blocks)
   lhbdc.py              LHBDC model mirror (Model, Network, MVCompressor, ResidualCompressor, Mask)
-  icip.py               ICIP2024 down-ratio search (prediction_flowonly, get_best_down_ratio_prediction)
+  icip.py               ICIP2024 down-ratio search, deformable alignment, ELIC checkerboard context loop
+  flowguided.py         ICIP2024 model mirror (FlowGuidedB, Offset_ELIC, Res_ELIC, ...) + its sequence coding loop
   ojsp.py               OJSP2025 down-sampling-ratio search (optimize_down_sampling_ratio, warp_psnr)
   flexrate.py           Flex-Rate model mirror (BidirFlowRef, Gain_Module, FlowCompressor, ResidualCompressor, UNet)
   patch.py              patch(model): swap the kernels into a model built from the reference's own classes
@@ -15,7 +16,7 @@ Layout
   gop.py / dist.py      hierarchical-GOP schedule, GOP sharding over ranks, record gathering
   synthetic.py          seeded synthetic video + weight calibration (no datasets / checkpoints offline)
 """
-from . import _lib, coding, dist, flexrate, gop, icip, lhbdc, modules, ojsp, ops, synthetic  # noqa: F401
+from . import _lib, coding, dist, flexrate, flowguided, gop, icip, lhbdc, modules, ojsp, ops, synthetic  # noqa: F401
 from .flexrate import BidirFlowRef  # noqa: F401
 from .lhbdc import Model, decode_B, encode_B, encode_B_symbols  # noqa: F401
 from .patch import patch  # noqa: F401

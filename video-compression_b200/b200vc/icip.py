@@ -125,11 +125,13 @@ ELIC_GROUPS = (6, 6, 12, 24, None)  # compression_bottlenecks.py:229-235: channe
 
 
 def elic_context_likelihoods(y, hyper_params, context_prediction_models, channel_context_models, entropy_parameters,
-                             gaussian_conditional, group_sizes=ELIC_GROUPS, inv_gain=None):
+                             gaussian_conditional, group_sizes=ELIC_GROUPS, inv_gain=None, bits_only=False):
     """The channel-group x checkerboard entropy loop of ``Offset_ELIC`` / ``Res_ELIC``
     (ICIP2024/src/model/compression_bottlenecks.py:229-269, :471-511) with the reference's own sub-modules.
 
-    Returns ``({"y_0": lik, ...}, y_hat)`` where ``y_hat = ste_round(y) * inv_gain`` (``inv_gain`` [M] or None).
+    Returns ``({"y_0": lik, ...}, y_hat)`` where ``y_hat = ste_round(y) * inv_gain`` (``inv_gain`` [M] or None); with
+    ``bits_only=True`` the first element is ``bits[N]`` (float64, sum of -log2 of every group's likelihoods) and no
+    likelihood tensor is written.
     The latent is quantised ONCE (K-CHK ``round_checker``: rounded + anchor-zeroed copies; every group and every
     "earlier groups" context input is a channel slice of those), the context convolution's output is checkerboard-
     masked straight into the entropy-parameter network's input buffer (``checker_mask``), and the likelihoods come
@@ -145,7 +147,7 @@ def elic_context_likelihoods(y, hyper_params, context_prediction_models, channel
     if start != M:
         raise ValueError(f"channel groups {group_sizes} do not cover {M} channels")
     y_hat, y_half = ops.round_checker(y)
-    likelihoods = {}
+    likelihoods, bits = {}, None
     for i, (a, b) in enumerate(sizes):
         ctx = context_prediction_models[i](y_half[:, a:b])
         parts = [ctx.shape[1]]
@@ -160,8 +162,15 @@ def elic_context_likelihoods(y, hyper_params, context_prediction_models, channel
             buf[:, parts[0]:parts[0] + parts[1]] = chan
         buf[:, -parts[-1]:] = hyper_params
         scales_hat, means_hat = entropy_parameters[i](buf).chunk(2, 1)
-        _, lik = gaussian_conditional(y[:, a:b], scales_hat, means=means_hat)
-        likelihoods[f"y_{i}"] = lik
+        if bits_only:
+            from . import modules as M_
+            r = ops.gauss_cond(y[:, a:b].contiguous(), scales_hat, means_hat,
+                               scale_bound=M_._scale_bound(gaussian_conditional),
+                               lik_bound=M_._lik_bound(gaussian_conditional), want_y_hat=False, want_lik=False)
+            bits = r["bits"] if bits is None else bits + r["bits"]
+        else:
+            _, lik = gaussian_conditional(y[:, a:b], scales_hat, means=means_hat)
+            likelihoods[f"y_{i}"] = lik
     if inv_gain is not None:
         y_hat = y_hat * inv_gain.view(1, -1, 1, 1)
-    return likelihoods, y_hat
+    return (bits if bits_only else likelihoods), y_hat

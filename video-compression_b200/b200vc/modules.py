@@ -436,3 +436,70 @@ class MeanScaleHyperprior(nn.Module):
         if scale_table is None:
             scale_table = get_scale_table()
         return self.gaussian_conditional.update_scale_table(scale_table, force=force)
+
+
+# ------------------------------------------------------------------- joint autoregressive container (ICIP codecs)
+def _conv5(i, o, stride=2):
+    return nn.Conv2d(i, o, kernel_size=5, stride=stride, padding=2)
+
+
+def _deconv5(i, o, stride=2):
+    return nn.ConvTranspose2d(i, o, kernel_size=5, stride=stride, output_padding=stride - 1, padding=2)
+
+
+class MaskedConv2d(nn.Conv2d):
+    """compressai.layers.MaskedConv2d (causal PixelCNN mask).  Present in the ICIP checkpoints as
+    ``context_prediction`` (created by the base class below), never called by those models."""
+
+    def __init__(self, *args, mask_type="A", **kwargs):
+        super().__init__(*args, **kwargs)
+        self.register_buffer("mask", torch.ones_like(self.weight.data))
+        _, _, h, w = self.mask.size()
+        self.mask[:, :, h // 2, w // 2 + (mask_type == "B"):] = 0
+        self.mask[:, :, h // 2 + 1:] = 0
+
+    def forward(self, x):
+        self.weight.data *= self.mask
+        return super().forward(x)
+
+
+class CheckerboardContext(nn.Conv2d):
+    """ICIP2024/src/model/layers.py:6-29: 5x5 context convolution restricted to the anchor checkerboard.  The
+    reference re-multiplies the weight by the mask on every call (quirk B.9); masking is idempotent, so here it is
+    applied once per weight version."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.register_buffer("mask", torch.zeros_like(self.weight.data))
+        self.mask[:, :, 0::2, 1::2] = 1
+        self.mask[:, :, 1::2, 0::2] = 1
+
+    def forward(self, x):
+        key = _pkey(self.weight)
+        if self.__dict__.get("_b200vc_masked") != key:
+            with torch.no_grad():
+                self.weight.mul_(self.mask)
+            self.__dict__["_b200vc_masked"] = _pkey(self.weight)
+        return super().forward(x)
+
+
+class JointAutoregressiveHierarchicalPriors(MeanScaleHyperprior):
+    """compressai.models.JointAutoregressiveHierarchicalPriors: the base class of the ICIP codecs' ``Offset_ELIC`` /
+    ``Res_ELIC`` (ICIP2024/src/model/compression_bottlenecks.py:72,313).  The subclasses replace ``h_a``, ``h_s`` and
+    ``entropy_parameters`` and never call ``g_a``, ``g_s`` or ``context_prediction``; the members are built as
+    CompressAI builds them so that reference checkpoints load with ``strict=True``."""
+
+    def __init__(self, N=192, M=192, **kwargs):
+        super().__init__(N=N, M=M)
+        self.g_a = nn.Sequential(_conv5(3, N), GDN(N), _conv5(N, N), GDN(N), _conv5(N, N), GDN(N), _conv5(N, M))
+        self.g_s = nn.Sequential(_deconv5(M, N), GDN(N, inverse=True), _deconv5(N, N), GDN(N, inverse=True),
+                                 _deconv5(N, N), GDN(N, inverse=True), _deconv5(N, 3))
+        self.h_a = nn.Sequential(nn.Conv2d(M, N, 3, 1, 1), nn.LeakyReLU(inplace=True), _conv5(N, N),
+                                 nn.LeakyReLU(inplace=True), _conv5(N, N))
+        self.h_s = nn.Sequential(_deconv5(N, M), nn.LeakyReLU(inplace=True), _deconv5(M, M * 3 // 2),
+                                 nn.LeakyReLU(inplace=True), nn.Conv2d(M * 3 // 2, M * 2, 3, 1, 1))
+        self.entropy_parameters = nn.Sequential(
+            nn.Conv2d(M * 12 // 3, M * 10 // 3, 1), nn.LeakyReLU(inplace=True),
+            nn.Conv2d(M * 10 // 3, M * 8 // 3, 1), nn.LeakyReLU(inplace=True), nn.Conv2d(M * 8 // 3, M * 6 // 3, 1))
+        self.context_prediction = MaskedConv2d(M, 2 * M, kernel_size=5, padding=2, stride=1)
+        self.gaussian_conditional = GaussianConditional(None)
