@@ -57,6 +57,9 @@ def parse():
                          "the ranks (SURVEY 8e); a step = the whole sequence")
     ap.add_argument("--conv-tf32", action="store_true",
                     help="let cuDNN use TF32 for the (out-of-scope) convolutions, as torch defaults do")
+    ap.add_argument("--deterministic", action="store_true",
+                    help="cudnn.benchmark off (the reference turns it on, LHBDC/test/testing.py:31): algorithm choice then "
+                         "depends on shapes only, so totals are bit-identical for any world size")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end timed region (profiling runs)")
     ap.add_argument("--ncu-range", action="store_true",
@@ -930,7 +933,7 @@ def run_product(args):
     torch.cuda.set_device(device)
     torch.backends.cudnn.allow_tf32 = bool(args.conv_tf32)
     torch.backends.cuda.matmul.allow_tf32 = False
-    torch.backends.cudnn.benchmark = True  # as LHBDC/test/testing.py:31
+    torch.backends.cudnn.benchmark = not args.deterministic  # on: as LHBDC/test/testing.py:31
 
     steps, warmup = max(1, args.steps), max(3, args.warmup)
     wl = REGISTRY[args.workload](args)

@@ -193,9 +193,10 @@ B200VC_API int b200vc_gdn_prepare_f32(const float* beta, const float* gamma, flo
  *   is the fast path (in-place residual add: the tensor-core kernel accumulates with a TMA reduce-add).
  *   out_i = x_i * rsqrt(beta_i + sum_j gamma_ij x_j^2)    (inverse == 1: * sqrt; inverse == 2, diagnostics:
  *   out_i = the norm beta_i + sum_j gamma_ij x_j^2 itself).
- *   impl: 0 = auto (2 when C == 128 and HW % 4 == 0, else 1), 1 = CUDA-core fp32 kernel (C in {64, 128, 192};
- *   bit-identical to the reference's fp32 chain), 2 = tcgen05 3xTF32 kernel (C == 128; <= 1.6e-6 relative: split
- *   products plus raw MUFU rsqrt / sqrt on the always-positive norm).  Other C return B200VC_EUNSUPPORTED.
+ *   impl: 0 = auto (2 when C in {128, 192} and HW % 4 == 0, else 1), 1 = CUDA-core fp32 kernel (C in {64, 128, 192};
+ *   bit-identical to the reference's fp32 chain), 2 = tcgen05 3xTF32 kernel (C == 128: gamma resident in TMEM;
+ *   C == 192: output channels split over CTA pairs; <= 2.5e-6 relative: split products plus raw MUFU rsqrt / sqrt on
+ *   the always-positive norm).  Other C return B200VC_EUNSUPPORTED.
  */
 B200VC_API int b200vc_gdn_f32(const float* x, const float* params, const float* addend, float* out, int N, int C,
                    int64_t HW, int inverse, int impl, void* stream);

@@ -33,7 +33,8 @@ def _x(N, C, H, W, seed=1):
 @pytest.mark.parametrize("impl", [1, 0])
 @pytest.mark.parametrize("inverse", [False, True])
 @pytest.mark.parametrize("C,shape", [(128, (1, 68, 120)), (128, (2, 33, 47)), (128, (1, 5, 8)), (64, (1, 40, 64)),
-                                     (192, (1, 34, 60)), (128, (1, 136, 240))])
+                                     (192, (1, 34, 60)), (128, (1, 136, 240)), (192, (1, 5, 8)), (192, (2, 40, 52)),
+                                     (192, (3, 17, 20)), (192, (1, 136, 240))])
 def test_gdn_matches_oracle(strict_fp32, impl, inverse, C, shape):
     from b200vc import modules, ops
     o, p = _pair(C, inverse, trained_like=True)
@@ -59,13 +60,14 @@ def test_gdn_at_init_closed_form_and_addend(strict_fp32):
         assert torch.equal(fused, want)
 
 
+@pytest.mark.parametrize("C", [128, 192])
 @pytest.mark.parametrize("impl", [1, 2])
 @pytest.mark.parametrize("inverse", [False, True])
-def test_gdn_residual_add_both_forms(strict_fp32, impl, inverse):
+def test_gdn_residual_add_both_forms(strict_fp32, impl, inverse, C):
     """out = gdn(x) + addend: separate output buffer vs in-place accumulation (TMA reduce-add on tcgen05)."""
     from b200vc import _lib, modules, ops
-    o, p = _pair(128, inverse, trained_like=True)
-    x = _x(2, 128, 37, 52)
+    o, p = _pair(C, inverse, trained_like=True)
+    x = _x(2, C, 37, 52)
     skip = torch.randn_like(x)
     params = modules.gdn_params(p)
     with torch.no_grad():
@@ -74,7 +76,7 @@ def test_gdn_residual_add_both_forms(strict_fp32, impl, inverse):
     scale = (base.abs() + skip.abs()).clamp(min=1e-3)  # the sum may cancel: judge against the summands
     inplace = ops.gdn(x, params, inverse=inverse, addend=skip.clone(), impl=impl)
     out = torch.empty_like(x)
-    rc = _lib.load().b200vc_gdn_f32(x.data_ptr(), params.data_ptr(), skip.data_ptr(), out.data_ptr(), 2, 128,
+    rc = _lib.load().b200vc_gdn_f32(x.data_ptr(), params.data_ptr(), skip.data_ptr(), out.data_ptr(), 2, C,
                                     37 * 52, int(inverse), impl, torch.cuda.current_stream().cuda_stream)
     assert rc == 0
     for got in (inplace, out):
@@ -109,6 +111,27 @@ def test_gdn_full_hd_layer_and_determinism(strict_fp32):
     print(f"gdn 544x960: max rel err {err:.3e}")
     assert err < 1e-5
     assert torch.equal(got, again)
+
+
+def test_gdn_c192_tensor_core_layer(strict_fp32):
+    """C = 192 (mbt2018_mean at quality >= 5; the joint-autoregressive base class) on the tcgen05 kernel: the second GDN
+    of a 1080p I-frame analysis transform, [1,192,272,480]; deterministic; batch- and position-permutation invariant."""
+    from b200vc import modules, ops
+    o, p = _pair(192, False, trained_like=True)
+    params = modules.gdn_params(p)
+    x = _x(2, 192, 272, 480)
+    with torch.no_grad():
+        want = o(x)
+    got = ops.gdn(x, params, impl=2)
+    err = ((got - want).abs() / want.abs().clamp(min=1e-6)).max().item()
+    print(f"gdn C=192 272x480 (tcgen05): max rel err {err:.3e}")
+    assert err < 1e-5
+    assert torch.equal(ops.gdn(x, params, impl=2), got)
+    assert torch.equal(ops.gdn(x[1:2].contiguous(), params, impl=2), got[1:2])
+    assert torch.equal(ops.gdn(x.flip(-1).contiguous(), params, impl=2), got.flip(-1))
+    assert torch.equal(ops.gdn(x, params), got)                       # auto == tcgen05 for C = 192
+    exact = ops.gdn(x, params, impl=1)
+    assert ((got - exact).abs() <= 1e-5 * exact.abs() + 1e-12).all()
 
 
 def test_gdn_unsupported_channels_raise():

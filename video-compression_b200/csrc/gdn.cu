@@ -15,7 +15,9 @@
 namespace b200vc {
 
 int launch_gdn_tc(const float* x, const float* params, const float* addend, float* out, int N, int C, int64_t HW,
-                  int inverse, cudaStream_t st);  // gdn_tc.cu
+                  int inverse, cudaStream_t st);
+int launch_gdn_tc192(const float* x, const float* params, const float* addend, float* out, int N, int64_t HW,
+                     int inverse, cudaStream_t st);  // gdn_tc192.cu  // gdn_tc.cu
 
 // params: [0,C) beta | [C, C+C^2) gamma[i][j] | [C+C^2, C+2C^2) gammaT[j][i] | [C+2C^2, C+4C^2) tf32 hi[i][j], lo[i][j]
 __host__ __device__ inline int64_t gdn_off_gamma(int C) { return C; }
@@ -219,8 +221,9 @@ extern "C" int b200vc_gdn_f32(const float* x, const float* params, const float* 
                      (addend == nullptr || (reinterpret_cast<uintptr_t>(addend) & 15u) == 0),
                  "gdn_f32: pointers must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  if (impl == 2 || (impl == 0 && C == 128 && HW % 4 == 0)) {
-    const int rc = launch_gdn_tc(x, params, addend, out, N, C, HW, inverse, st);
+  if (impl == 2 || (impl == 0 && (C == 128 || C == 192) && HW % 4 == 0)) {
+    const int rc = C == 192 ? launch_gdn_tc192(x, params, addend, out, N, HW, inverse, st)
+                            : launch_gdn_tc(x, params, addend, out, N, C, HW, inverse, st);
     if (rc != B200VC_EUNSUPPORTED || impl == 2) return rc;
   }
   switch (C) {
