@@ -97,6 +97,20 @@ B200VC_API int b200vc_warp2_lhbdc_f32(const float* x_before, const float* x_afte
                            const float* tab_y, float* out, float* flows_out, int N, int H, int W, int h4,
                            int w4, int arith, void* stream);
 
+/* Flex-Rate form of the fused motion compensation (Flex-Rate-Hier-Bidir-Video-Compression/b_model/b_model.py:34-45
+ * `process`, :58-66 in `forward`): flow glue + both FLEX warps (zeros padding, half-pixel grid, :99-112) + the 16-channel
+ * concat cat(ft0, ft1, x0, x1, warp(x0, ft0), warp(x1, ft1)) in one pass.
+ *   mode 0 (linear motion): fa = Flow_0_1, fb = Flow_1_0 (each [N,2,H,W] with batch stride fa_bs / fb_bs: the two halves
+ *     of the flow predictor's 4-channel output), ft0 = a0*fa + b0*fb, ft1 = a1*fa + b1*fb with the reference's
+ *     coefficients a0 = -(1-t)t, b0 = t*t, a1 = (1-t)(1-t), b1 = -t(1-t) (python floats cast to fp32 by the caller);
+ *   mode 1 (refinement): fa = cat(mv_before, mv_after), fb = flow_hat[:, 0:4] (each [N,4,H,W] with batch stride):
+ *     ft0 = fa[0:2] + fb[0:2], ft1 = fa[2:4] + fb[2:4]; a0..b1 ignored.
+ *   x0, x1 [N,3,H,W] contiguous; out16 [N,16,H,W] contiguous.
+ */
+B200VC_API int b200vc_warp2_flex_f32(const float* x0, const float* x1, const float* fa, int64_t fa_bs, const float* fb,
+                                     int64_t fb_bs, int mode, float a0, float b0, float a1, float b1, float* out16,
+                                     int N, int H, int W, void* stream);
+
 /* Search form (ICIP2024/src/opt_helpers.py:23-51: prediction_flowonly + clamp + MSE per candidate down-ratio;
  * OJSP2025/video_model.py:621-666): both warps + 0.5/0.5 blend + clamp + squared error against x_cur in one pass.
  *   x1, x2, x_cur [N,3,H,W]; flow1, flow2 [N,2,H,W]; pred (nullable) [N,3,H,W];

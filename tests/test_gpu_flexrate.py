@@ -64,6 +64,31 @@ def test_flexrate_compressor_api_and_batch(models):
     assert ((by + bz - tot).abs() / tot).max().item() < 1e-6
 
 
+@pytest.mark.parametrize("shape", [(1, 128, 192), (2, 37, 53), (1, 1088, 1920), (3, 8, 8)])
+def test_fused_flex_warp2_is_bit_exact(shape):
+    """K-WARP2 (Flex form) vs the reference chain (b_model.py:34-45 and :58-66): linear-motion glue / refinement add,
+    two zero-padded half-pixel warps and the 16-channel concat, bit for bit -- incl. vectors far outside the frame."""
+    from b200vc import ops
+    from oracle import warp as o_warp
+    N, H, W = shape
+    g = torch.Generator().manual_seed(31 + H)
+    x0, x1 = torch.rand(N, 3, H, W, generator=g).cuda(), torch.rand(N, 3, H, W, generator=g).cuda()
+    flow = (4.0 * torch.randn(N, 4, H, W, generator=g)).cuda()
+    far = (torch.rand(N, 1, H, W, generator=g) < 0.02).cuda()
+    flow = torch.where(far, flow * 500.0, flow)
+    for t in (0.5, 0.3):
+        f01, f10 = flow[:, :2], flow[:, 2:4]
+        ft0 = -(1 - t) * t * f01 + t * t * f10
+        ft1 = (1 - t) * (1 - t) * f01 - t * (1 - t) * f10
+        want = torch.cat((ft0, ft1, x0, x1, o_warp.backwarp_flex(x0, ft0), o_warp.backwarp_flex(x1, ft1)), 1)
+        got = ops.warp2_flex(x0, x1, flow[:, 0:2], flow[:, 2:4], "linear", t)
+        assert torch.equal(got, want), f"linear-motion form differs at t={t}"
+    delta = torch.randn(N, 5, H, W, generator=g).cuda()          # flow compressor output (only 0:4 used)
+    mvb, mva = got[:, 0:2] + delta[:, 0:2], got[:, 2:4] + delta[:, 2:4]
+    want = torch.cat((mvb, mva, x0, x1, o_warp.backwarp_flex(x0, mvb), o_warp.backwarp_flex(x1, mva)), 1)
+    assert torch.equal(ops.warp2_flex(x0, x1, got[:, 0:4], delta[:, 0:4], "refine"), want)
+
+
 def test_patch_rebinds_flex_backwarp(models):
     import copy
 

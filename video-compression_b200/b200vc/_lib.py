@@ -25,6 +25,7 @@ _SIGNATURES = {
     "b200vc_reduce_blocks": (c_int, [c_int64]),
     "b200vc_warp_f32": (c_int, [_fp, c_int64, _fp, _fp, _fp, _fp, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "b200vc_warp2_lhbdc_f32": (c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "b200vc_warp2_flex_f32": (c_int, [_fp, _fp, _fp, c_int64, _fp, c_int64, c_int, c_float, c_float, c_float, c_float, _fp, c_int, c_int, c_int, c_void_p]),
     "b200vc_warp2_half_sse_blocks": (c_int, [c_int, c_int]),
     "b200vc_warp2_half_sse_f32": (c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, c_int, c_int, c_int, c_int, c_void_p]),
     "b200vc_warp_sse_f32": (c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, c_int, c_int, c_int, c_int, c_void_p]),

@@ -183,27 +183,16 @@ class BidirFlowRef(nn.Module):
         return ops.backwarp(img, flow, "flex")
 
     def process(self, x0, x1, t=0.5):
-        N, _, H, W = x0.shape
+        """b_model.py:34-45: flow predictor, then K-WARP2 (Flex form): linear-motion glue + both warps + concat."""
         flow = self.flow_predictor(torch.cat((x0, x1), 1))
-        f01, f10 = flow[:, :2], flow[:, 2:4]
-        ft0 = -(1 - t) * t * f01 + t * t * f10
-        ft1 = (1 - t) * (1 - t) * f01 - t * (1 - t) * f10
-        conc = torch.empty((N, 16, H, W), device=x0.device, dtype=x0.dtype)  # cat(ft0, ft1, x0, x1, xt1, xt2)
-        conc[:, 0:2], conc[:, 2:4], conc[:, 4:7], conc[:, 7:10] = ft0, ft1, x0, x1
-        ops.backwarp(x0, ft0, "flex", out=conc[:, 10:13])
-        ops.backwarp(x1, ft1, "flex", out=conc[:, 13:16])
-        return ft0, ft1, conc
+        conc = ops.warp2_flex(x0, x1, flow[:, 0:2], flow[:, 2:4], "linear", t)   # cat(ft0, ft1, x0, x1, xt1, xt2)
+        return conc[:, 0:2], conc[:, 2:4], conc
 
     def forward_device(self, x_before, x_current, x_after, n, l):
-        N, _, H, W = x_current.shape
         mv_before, mv_after, x_conc = self.process(x_before, x_after)
         flow_hat, fy, fz = self.flow_compressor.forward_bits(torch.cat((x_conc, x_current), 1), n, l)
-        temp = torch.empty((N, 16, H, W), device=x_current.device, dtype=x_current.dtype)
-        temp[:, 0:2] = mv_before + flow_hat[:, :2]
-        temp[:, 2:4] = mv_after + flow_hat[:, 2:4]
-        temp[:, 4:7], temp[:, 7:10] = x_before, x_after
-        ops.backwarp(x_before, temp[:, 0:2].contiguous(), "flex", out=temp[:, 10:13])
-        ops.backwarp(x_after, temp[:, 2:4].contiguous(), "flex", out=temp[:, 13:16])
+        # mv refinement + both warps + the mask net's 16-channel input (b_model.py:58-66), one kernel
+        temp = ops.warp2_flex(x_before, x_after, x_conc[:, 0:4], flow_hat[:, 0:4], "refine")
         logits = self.Mask(temp)
         x_comp, residual, _ = ops.blend_residual("normw", logits, temp[:, 10:13], temp[:, 13:16], x_current)
         res_hat, ry, rz = self.residual_compressor.forward_bits(residual, n, l)

@@ -233,6 +233,36 @@ def warp2_lhbdc(x_before, x_after, flow_hat, flow_ab, flow_ba, return_flows=Fals
     return (out, flows) if return_flows else out
 
 
+def warp2_flex(x0, x1, fa, fb, mode, t=0.5):
+    """Fused Flex-Rate motion compensation (b_model.py:34-45 and :58-66) -> the 16-channel buffer
+    cat(ft0, ft1, x0, x1, backwarp(x0, ft0), backwarp(x1, ft1)).
+    mode 'linear': fa = Flow_0_1, fb = Flow_1_0 ([N,2,H,W] each; channel slices of the predictor output are fine),
+    ft0 = -(1-t)t*fa + t*t*fb, ft1 = (1-t)(1-t)*fa - t(1-t)*fb.
+    mode 'refine': fa = cat(mv_before, mv_after) (e.g. channels 0:4 of the previous buffer), fb = flow_hat[:, 0:4]."""
+    x0 = _contig(x0, "warp2_flex(x0)")
+    x1 = _contig(x1, "warp2_flex(x1)")
+    N, C, H, W = x0.shape
+    cf = 2 if mode == "linear" else 4
+    if mode not in ("linear", "refine"):
+        raise ValueError(f"warp2_flex: unknown mode {mode!r}")
+    if C != 3 or x1.shape != x0.shape:
+        raise RuntimeError("warp2_flex: references must both be [N,3,H,W]")
+    fa, pa, abs_ = _planes(fa, "warp2_flex(fa)")
+    fb, pb, bbs = _planes(fb, "warp2_flex(fb)")
+    if tuple(fa.shape) != (N, cf, H, W) or tuple(fb.shape) != (N, cf, H, W):
+        raise RuntimeError(f"warp2_flex: flow inputs must be [N,{cf},H,W] for mode {mode!r}")
+    out = torch.empty((N, 16, H, W), device=x0.device, dtype=torch.float32)
+    if N == 0:
+        return out
+    # the reference multiplies fp32 tensors by python floats: the scalar is cast to fp32, each product rounded once
+    a0, b0, a1, b1 = -(1 - t) * t, t * t, (1 - t) * (1 - t), -(t * (1 - t))
+    lib = _lib.load()
+    _run("warp2_flex_f32", N * H * W * 4 * (6 + 2 * cf + 16), lambda: lib.b200vc_warp2_flex_f32(
+        x0.data_ptr(), x1.data_ptr(), pa, abs_, pb, bbs, 0 if mode == "linear" else 1, a0, b0, a1, b1, out.data_ptr(),
+        N, H, W, _stream()), tag=f"{N}x16x{H}x{W}")
+    return out
+
+
 def warp2_half_sse(x1, x2, flow1, flow2, x_cur, variant="ac1", want_pred=False):
     """Search form of ICIP2024/src/opt_helpers.py:23-51: warp both references, 0.5/0.5 blend, clamp, squared error
     against ``x_cur`` -- one kernel.  Returns (sse[N] float64, pred or None); MSE = sse / (3*H*W)."""

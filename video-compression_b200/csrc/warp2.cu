@@ -474,4 +474,124 @@ int launch_warp2_staged(const float* xb, const float* xa, const float* flow_hat,
   return check_launch("warp2_lhbdc_f32(staged)");
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// K-WARP2 (Flex-Rate form): the flow glue of BidirFlowRef + both FLEX backward warps + the 16-channel concat the
+// flow compressor / mask U-Net consume, in one pass (Flex-Rate.../b_model/b_model.py:34-45 `process` and :58-66):
+//   LINEAR  ft0 = c.a0*f01 + c.b0*f10 ; ft1 = c.a1*f01 + c.b1*f10   (linear-motion flows to the middle frame; the
+//           reference's python-float coefficients -(1-t)t, t^2, (1-t)^2, -t(1-t) arrive as fp32, each product and
+//           each sum rounded once, as torch's separate elementwise kernels round)
+//   REFINE  ft0 = base[0:2] + delta[0:2] ; ft1 = base[2:4] + delta[2:4]   (mv_before + flow_hat[:, :2], ...)
+//   out16   = cat(ft0, ft1, x0, x1, backwarp(x0, ft0), backwarp(x1, ft1))
+// The reference materialises the two flows, two warped frames and the concat separately (and the first port copied
+// the flow channel slices with .contiguous() before each warp); here x0 / x1 are read once for both the copy and the
+// gathers.  FLEX warp = zeros padding, half-pixel grid 2((x+u)/W - 0.5) (b_model.py:99-112): taps are predicated, and
+// ATen's int-range guard on the unnormalised coordinate is kept because nothing clips it.
+namespace wf {
+
+constexpr int kTX = 128, kTY = 8, kThreads = 256, kPX = 4;
+
+struct Coef {
+  float a0, b0, a1, b1;
+};
+
+template <bool LINEAR>
+__global__ void __launch_bounds__(kThreads, 2)
+warp2_flex_kernel(const float* __restrict__ x0p, const float* __restrict__ x1p, const float* __restrict__ fa,
+                  int64_t fa_bs, const float* __restrict__ fb, int64_t fb_bs, Coef cf, float* __restrict__ out, int N,
+                  WarpGeom g) {
+  const int n = blockIdx.z;
+  const int y = blockIdx.y * kTY + (threadIdx.x >> 5);
+  if (y >= g.H) return;
+  const int lane = threadIdx.x & 31;
+  const int bx = blockIdx.x * kTX;
+  const int HW = g.H * g.W;
+  const float* ia[2] = {x0p + (int64_t)n * 3 * HW, x1p + (int64_t)n * 3 * HW};
+  const float* pa = fa + (int64_t)n * fa_bs;
+  const float* pb = fb + (int64_t)n * fb_bs;
+  float* po = out + (int64_t)n * 16 * HW;
+#pragma unroll 1
+  for (int j = 0; j < kPX; ++j) {
+    const int x = bx + lane + 32 * j;
+    if (x >= g.W) break;
+    const int o = y * g.W + x;
+    float f[4];   // ft0.x, ft0.y, ft1.x, ft1.y
+    if (LINEAR) {
+      const float ax = __ldg(pa + o), ay = __ldg(pa + HW + o), bxv = __ldg(pb + o), byv = __ldg(pb + HW + o);
+      f[0] = __fadd_rn(__fmul_rn(cf.a0, ax), __fmul_rn(cf.b0, bxv));
+      f[1] = __fadd_rn(__fmul_rn(cf.a0, ay), __fmul_rn(cf.b0, byv));
+      f[2] = __fadd_rn(__fmul_rn(cf.a1, ax), __fmul_rn(cf.b1, bxv));
+      f[3] = __fadd_rn(__fmul_rn(cf.a1, ay), __fmul_rn(cf.b1, byv));
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) f[c] = __fadd_rn(__ldg(pa + c * HW + o), __ldg(pb + c * HW + o));
+    }
+    Taps t[2];
+#pragma unroll
+    for (int dir = 0; dir < 2; ++dir) {
+      float ix, iy;
+      coords<B200VC_WARP_FLEX, true>(g, x, y, f[2 * dir], f[2 * dir + 1], 0.f, 0.f, ix, iy);
+      t[dir] = make_taps<false>(ix, iy, g.H, g.W);
+    }
+    float ctr[2][3], v[2][3][4];
+#pragma unroll
+    for (int dir = 0; dir < 2; ++dir) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float* p = ia[dir] + c * HW;
+        ctr[dir][c] = __ldg(p + o);                 // the frame itself (channels 4..9 of the concat)
+        v[dir][c][0] = __ldg(p + t[dir].o00);       // invalid taps read element 0 and are not accumulated
+        v[dir][c][1] = __ldg(p + t[dir].o01);
+        v[dir][c][2] = __ldg(p + t[dir].o10);
+        v[dir][c][3] = __ldg(p + t[dir].o11);
+      }
+    }
+    // scheduling fence (see w2::warp2_kernel): every gather of the pixel is issued before the first FMA chain
+    int any = 0;
+#pragma unroll
+    for (int dir = 0; dir < 2; ++dir)
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        any |= __float_as_int(v[dir][c][0]) | __float_as_int(v[dir][c][1]) | __float_as_int(v[dir][c][2]) |
+               __float_as_int(v[dir][c][3]);
+    const float zero = __int_as_float(any & g.arith);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) __stcg(po + c * HW + o, f[c]);
+#pragma unroll
+    for (int dir = 0; dir < 2; ++dir) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        __stcg(po + (4 + 3 * dir + c) * HW + o, ctr[dir][c]);
+        // ATen: out_acc = 0; out_acc += v * w for every in-bounds tap, in nw, ne, sw, se order
+        float acc = zero;
+        if (t[dir].v00) acc = __fmaf_rn(v[dir][c][0], t[dir].w00, acc);
+        if (t[dir].v01) acc = __fmaf_rn(v[dir][c][1], t[dir].w01, acc);
+        if (t[dir].v10) acc = __fmaf_rn(v[dir][c][2], t[dir].w10, acc);
+        if (t[dir].v11) acc = __fmaf_rn(v[dir][c][3], t[dir].w11, acc);
+        __stcg(po + (10 + 3 * dir + c) * HW + o, acc);
+      }
+    }
+  }
+}
+
+}  // namespace wf
 }  // namespace b200vc
+
+using namespace b200vc;
+
+extern "C" int b200vc_warp2_flex_f32(const float* x0, const float* x1, const float* fa, int64_t fa_bs, const float* fb,
+                                     int64_t fb_bs, int mode, float a0, float b0, float a1, float b1, float* out16, int N,
+                                     int H, int W, void* stream) {
+  B200VC_REQUIRE(x0 && x1 && fa && fb && out16, "warp2_flex_f32: null pointer");
+  B200VC_REQUIRE(N > 0 && N <= 65535 && H > 0 && W > 0, "warp2_flex_f32: bad shape");
+  B200VC_REQUIRE(mode == 0 || mode == 1, "warp2_flex_f32: mode must be 0 (linear motion) or 1 (refine), got %d", mode);
+  B200VC_REQUIRE((int64_t)H * W * 16 < (1ll << 31), "warp2_flex_f32: plane too large");
+  const WarpGeom g = make_geom(H, W, B200VC_WARP_FLEX, 0);
+  dim3 grid((W + wf::kTX - 1) / wf::kTX, (H + wf::kTY - 1) / wf::kTY, N);
+  const wf::Coef cf{a0, b0, a1, b1};
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mode == 0)
+    wf::warp2_flex_kernel<true><<<grid, wf::kThreads, 0, st>>>(x0, x1, fa, fa_bs, fb, fb_bs, cf, out16, N, g);
+  else
+    wf::warp2_flex_kernel<false><<<grid, wf::kThreads, 0, st>>>(x0, x1, fa, fa_bs, fb, fb_bs, cf, out16, N, g);
+  return check_launch("warp2_flex_f32");
+}
