@@ -9,10 +9,24 @@ latents span several integer bins and scales cover the 64-entry table.  It is pu
 state dict (no forward pass), so it applies identically to this package's ``lhbdc.Model`` and to any model
 with the reference's key layout.
 """
+import contextlib
 import math
 
 import torch
 import torch.nn.functional as F
+
+
+@contextlib.contextmanager
+def _one_thread():
+    """CPU ``F.interpolate`` rounds differently for different intra-op thread counts (vector-path boundaries move), and
+    torchrun sets OMP_NUM_THREADS=1 per rank: build the canvas single-threaded so that a 1-process and an N-process
+    run see bit-identical frames."""
+    n = torch.get_num_threads()
+    torch.set_num_threads(1)
+    try:
+        yield
+    finally:
+        torch.set_num_threads(n)
 
 
 @torch.no_grad()
@@ -102,11 +116,12 @@ def make_sequence(T, H=1080, W=1920, seed=1234, device="cpu", max_motion=8, nois
     g = torch.Generator().manual_seed(seed)
     margin = max_motion * 2 + 8
     ch, cw = (H + 2 * margin + 31) // 32, (W + 2 * margin + 31) // 32
-    coarse = torch.rand(1, 3, ch + 1, cw + 1, generator=g)
-    canvas = F.interpolate(coarse, size=((ch + 1) * 32, (cw + 1) * 32), mode="bicubic", align_corners=False)
-    fine = torch.rand(1, 3, (ch + 1) * 4, (cw + 1) * 4, generator=g)
-    canvas = (0.8 * canvas + 0.2 * F.interpolate(fine, size=canvas.shape[-2:], mode="bilinear",
-                                                 align_corners=False)).clamp_(0, 1)[0]
+    with _one_thread():
+        coarse = torch.rand(1, 3, ch + 1, cw + 1, generator=g)
+        canvas = F.interpolate(coarse, size=((ch + 1) * 32, (cw + 1) * 32), mode="bicubic", align_corners=False)
+        fine = torch.rand(1, 3, (ch + 1) * 4, (cw + 1) * 4, generator=g)
+        canvas = (0.8 * canvas + 0.2 * F.interpolate(fine, size=canvas.shape[-2:], mode="bilinear",
+                                                     align_corners=False)).clamp_(0, 1)[0]
     frames = torch.empty(T, 3, H, W)
     for t in range(T):
         dx = margin + int(round(max_motion * math.sin(0.37 * t)))
@@ -124,11 +139,12 @@ def make_frames(indices, H=1080, W=1920, seed=1234, device="cpu", max_motion=8, 
     g = torch.Generator().manual_seed(seed)
     margin = max_motion * 2 + 8
     ch, cw = (H + 2 * margin + 31) // 32, (W + 2 * margin + 31) // 32
-    coarse = torch.rand(1, 3, ch + 1, cw + 1, generator=g)
-    canvas = F.interpolate(coarse, size=((ch + 1) * 32, (cw + 1) * 32), mode="bicubic", align_corners=False)
-    fine = torch.rand(1, 3, (ch + 1) * 4, (cw + 1) * 4, generator=g)
-    canvas = (0.8 * canvas + 0.2 * F.interpolate(fine, size=canvas.shape[-2:], mode="bilinear",
-                                                 align_corners=False)).clamp_(0, 1)[0]
+    with _one_thread():
+        coarse = torch.rand(1, 3, ch + 1, cw + 1, generator=g)
+        canvas = F.interpolate(coarse, size=((ch + 1) * 32, (cw + 1) * 32), mode="bicubic", align_corners=False)
+        fine = torch.rand(1, 3, (ch + 1) * 4, (cw + 1) * 4, generator=g)
+        canvas = (0.8 * canvas + 0.2 * F.interpolate(fine, size=canvas.shape[-2:], mode="bilinear",
+                                                     align_corners=False)).clamp_(0, 1)[0]
     indices = list(indices)
     frames = torch.empty(len(indices), 3, H, W)
     for k, t in enumerate(indices):
