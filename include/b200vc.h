@@ -215,10 +215,6 @@ B200VC_API int b200vc_gdn_prepare_f32(const float* beta, const float* gamma, flo
 B200VC_API int b200vc_gdn_f32(const float* x, const float* params, const float* addend, float* out, int N, int C,
                    int64_t HW, int inverse, int impl, void* stream);
 
-/* Diagnostics only: CTA 0 of the following tcgen05 GDN launches stamps clock64() per tile and pipeline event into
- * `device_buffer` (256 tiles x 16 slots of int64; NULL switches it off).  Used by tools/gdn_trace.py. */
-B200VC_API void b200vc_debug_set_gdn_trace(long long* device_buffer);
-
 /* ----------------------------------------------------------------------- Gaussian conditional (Q1, Q2, Q4, Q5)
  * Replaces GaussianConditional.forward / quantize("symbols") / build_indexes and the torch.log(lik).sum()
  * bit sums (LHBDC/model/layers.py:102-103; LHBDC/model/m.py:73-91; Flex-Rate.../b_model/layers.py:145-146).

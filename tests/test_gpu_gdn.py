@@ -164,3 +164,42 @@ def test_gdn_full_size_properties(strict_fp32, impl):
     z = ops.gdn(x, params, inverse=True, impl=impl)
     prod = (y.double() * z.double())
     assert ((prod - x.double() ** 2).abs() <= 1e-5 * x.double() ** 2 + 1e-30).all()
+
+
+def test_residual_block_stride1_keeps_its_input(strict_fp32):
+    """with stride 1 and in_ch == out_ch the identity IS the caller's input; the fused residual add must not
+    write into it (CompressAI's `out += identity` writes `out`)."""
+    from b200vc import modules
+    torch.manual_seed(3)
+    blk_o = cai.ResidualBlockWithStride(128, 128, stride=1).cuda().eval()
+    blk_p = modules.ResidualBlockWithStride(128, 128, stride=1).cuda().eval()
+    assert blk_p.skip is None
+    blk_p.load_state_dict(blk_o.state_dict())
+    x = _x(1, 128, 24, 36)
+    keep = x.clone()
+    with torch.no_grad():
+        got = blk_p(x)
+        want = blk_o(keep.clone())
+    assert torch.equal(x, keep), "the block overwrote its input"
+    assert ((got - want).abs() <= 1e-5 * want.abs() + 1e-6).all()
+
+
+def test_data_edits_need_and_get_cache_invalidation(strict_fp32):
+    """`.data` edits do not bump the tensor version: `invalidate_caches` (also run by update() and after
+    load_state_dict) drops the derived GDN operands."""
+    from b200vc import modules
+    o, p = _pair(128, False, trained_like=True)
+    x = _x(1, 128, 8, 12)
+    with torch.no_grad():
+        a = p(x)
+        p.beta.data.mul_(1.5)
+        o.beta.data.mul_(1.5)
+        modules.invalidate_caches(p)
+        b = p(x)
+        assert not torch.equal(a, b)
+        torch.testing.assert_close(b, o(x), rtol=1e-5, atol=1e-7)
+        sd = {k: v.clone() for k, v in p.state_dict().items()}
+        sd["beta"] = sd["beta"] * 0.5
+        p.load_state_dict(sd)
+        o.load_state_dict(sd)
+        torch.testing.assert_close(p(x), o(x), rtol=1e-5, atol=1e-7)

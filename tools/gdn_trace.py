@@ -13,6 +13,9 @@ import torch  # noqa: E402
 from b200vc import _lib, modules, ops  # noqa: E402
 
 lib = _lib.load()
+if not hasattr(lib, "b200vc_debug_set_gdn_trace"):
+    raise SystemExit("gdn_trace.py needs a debug build: NVCC_FLAGS=-DB200VC_ENABLE_GDN_TRACE python "
+                     "video-compression_b200/build.py --force   (include/b200vc_debug.h)")
 p = modules.GDN(128).cuda().eval()
 params = modules.gdn_params(p)
 x = torch.randn(1, 128, 544, 960, device="cuda")

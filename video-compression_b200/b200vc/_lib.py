@@ -38,7 +38,6 @@ _SIGNATURES = {
     "b200vc_gdn_params_floats": (c_int64, [c_int]),
     "b200vc_gdn_prepare_f32": (c_int, [_fp, _fp, c_float, c_float, c_float, _fp, c_int, c_void_p]),
     "b200vc_gdn_f32": (c_int, [_fp, _fp, _fp, _fp, c_int, c_int, c_int64, c_int, c_int, c_void_p]),
-    "b200vc_debug_set_gdn_trace": (None, [_fp]),
     "b200vc_gauss_cond_f32": (c_int, [_fp, _fp, _fp, c_int64, _fp, _fp, _fp, _fp, _fp, _fp, c_int, c_float, c_float, _fp, c_int, _fp, _fp, c_int, c_int, c_int64, c_void_p]),
     "b200vc_eb_prepare_f32": (c_int, [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), _fp, _fp, c_int, c_void_p]),
     "b200vc_entropy_bottleneck_f32": (c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, c_float, _fp, c_int, _fp, _fp, c_int, c_int, c_int64, c_void_p]),
@@ -69,6 +68,9 @@ def load():
         fn = getattr(lib, name)  # AttributeError here = header/library mismatch: fail loudly
         fn.restype = res
         fn.argtypes = args
+    if hasattr(lib, "b200vc_debug_set_gdn_trace"):  # debug builds only (include/b200vc_debug.h)
+        lib.b200vc_debug_set_gdn_trace.restype = None
+        lib.b200vc_debug_set_gdn_trace.argtypes = [_fp]
     _lib = lib
     return lib
 

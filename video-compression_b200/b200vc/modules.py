@@ -46,6 +46,22 @@ def _pkey(*tensors):
     return tuple((t.data_ptr(), t._version) for t in tensors)
 
 
+def invalidate_caches(module):
+    """Drop every derived-parameter cache (re-parametrised GDN operands, packed factorised-prior networks, CDF tables,
+    masked context weights) below ``module``.  The caches are keyed on (storage pointer, tensor version), which
+    ``param.copy_()`` / ``load_state_dict`` / optimiser steps bump -- but edits through ``param.data`` (the reference
+    style: ``weight.data.fill_(0.0)``, Flex-Rate.../b_model/layers.py:125-126) do not.  Called automatically after
+    ``load_state_dict`` and by ``update()``; call it yourself after a ``.data`` edit."""
+    for m in module.modules():
+        for k in [k for k in m.__dict__ if k.startswith("_b200vc_")]:
+            del m.__dict__[k]
+    return module
+
+
+def _invalidate_after_load(module, incompatible_keys=None):
+    invalidate_caches(module)
+
+
 # ------------------------------------------------------------------------------------------ GDN
 def gdn_params(mod):
     """Re-parametrised beta/gamma (+ operand images), recomputed only when the stored parameters change
@@ -56,8 +72,8 @@ def gdn_params(mod):
                                 mod.gamma_reparam.lower_bound.bound.item(), mod.beta_reparam.pedestal.item()))
 
 
-def gdn_forward(mod, x, addend=None):
-    return ops.gdn(x, gdn_params(mod), inverse=bool(mod.inverse), addend=addend)
+def gdn_forward(mod, x, addend=None, inplace=None):
+    return ops.gdn(x, gdn_params(mod), inverse=bool(mod.inverse), addend=addend, inplace=inplace)
 
 
 class LowerBound(nn.Module):
@@ -88,6 +104,7 @@ class GDN(nn.Module):
         self.beta = nn.Parameter(self.beta_reparam.init(torch.ones(in_channels)))
         self.gamma_reparam = NonNegativeParametrizer()
         self.gamma = nn.Parameter(self.gamma_reparam.init(float(gamma_init) * torch.eye(in_channels)))
+        self.register_load_state_dict_post_hook(_invalidate_after_load)
 
     forward = gdn_forward
 
@@ -107,8 +124,10 @@ def subpel_conv3x3(in_ch, out_ch, r=1):
 def res_stride_forward(mod, x):
     """ResidualBlockWithStride.forward with ``out += identity`` folded into the GDN kernel's epilogue."""
     out = mod.conv2(mod.leaky_relu(mod.conv1(x)))
-    identity = mod.skip(x) if mod.skip is not None else x
-    return gdn_forward(mod.gdn, out, addend=identity)
+    if mod.skip is not None:
+        return gdn_forward(mod.gdn, out, addend=mod.skip(x))      # the skip tensor is ours: accumulate into it
+    # stride 1, in_ch == out_ch: the identity IS the caller's input -- CompressAI's `out += identity` never writes x
+    return gdn_forward(mod.gdn, out, addend=x, inplace=False)
 
 
 def res_upsample_forward(mod, x):
@@ -165,6 +184,7 @@ class EntropyModel(nn.Module):
         self.register_buffer("_offset", torch.IntTensor())
         self.register_buffer("_quantized_cdf", torch.IntTensor())
         self.register_buffer("_cdf_length", torch.IntTensor())
+        self.register_load_state_dict_post_hook(_invalidate_after_load)
 
 
 def _lik_bound(mod):
@@ -432,7 +452,9 @@ class MeanScaleHyperprior(nn.Module):
 
     def update(self, scale_table=None, force=False):
         """Installs the Gaussian scale table (``model.mv_compressor.update(force=True)``, LHBDC/encode_B.py:34).
-        The quantised CDF rows are built lazily on the device at the first compress / decompress."""
+        The quantised CDF rows are built lazily on the device at the first compress / decompress; every derived
+        cache below this module is dropped (the reference calls ``update`` after loading / editing weights)."""
+        invalidate_caches(self)
         if scale_table is None:
             scale_table = get_scale_table()
         return self.gaussian_conditional.update_scale_table(scale_table, force=force)
@@ -473,6 +495,7 @@ class CheckerboardContext(nn.Conv2d):
         self.register_buffer("mask", torch.zeros_like(self.weight.data))
         self.mask[:, :, 0::2, 1::2] = 1
         self.mask[:, :, 1::2, 0::2] = 1
+        self.register_load_state_dict_post_hook(_invalidate_after_load)
 
     def forward(self, x):
         key = _pkey(self.weight)

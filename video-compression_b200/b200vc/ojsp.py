@@ -39,27 +39,22 @@ def warp_psnr(ref_frame, flow, x):
 
 
 def optimize_down_sampling_ratio(model, x, dpb, ratios=DOWNSAMPLING_RATIOS, bias=0.1):
-    """video_model.py:621-666 -> (best_est_mv_down, best_ratio).  Same selection rule: strict ``>`` keeps the earliest
-    best candidate; if the best PSNR beats the previous frame's ratio by less than ``bias`` dB the previous ratio
-    (``dpb["ref_down_ratio"]``) and its motion field are kept."""
+    """video_model.py:621-666 -> (best_est_mv_down, best_ratio).  Same selection rule: the running best starts at
+    -inf and only a strictly greater PSNR replaces it (the earliest best candidate wins, NaN never does); if the best
+    PSNR beats the previous frame's ratio (``dpb["ref_down_ratio"]``) by less than ``bias`` dB the previous ratio and its
+    motion field are kept.  Only the 32 PSNR scalars live through the sweep (the reference keeps two full-resolution
+    fields; keeping all 32 would be 2.1 GB at 2160 x 3840): the winning field is recomputed after the single sync."""
     ref = dpb["ref_frame"]
-    flows, psnrs = [], []
-    for ratio in ratios:
-        mv = candidate_flow(model, x, ref, ratio)
-        flows.append(mv)
-        psnrs.append(warp_psnr(ref, mv, x))
-    psnr = torch.stack(psnrs).float().cpu()              # the search's only host synchronisation
-    best = 0
-    for i in range(1, len(ratios)):
-        if psnr[i] > psnr[best]:
-            best = i
-    best_ratio, best_mv = ratios[best], flows[best]
     prev = dpb["ref_down_ratio"]
-    if prev in ratios:
-        j = list(ratios).index(prev)
-        if (psnr[best] - psnr[j]) < bias and prev != best_ratio:
-            best_ratio, best_mv = prev, flows[j]
-    else:
+    if prev not in ratios:
         # the reference leaves prev_ratio_psnr unbound in this case (UnboundLocalError at video_model.py:657)
         raise ValueError(f"dpb['ref_down_ratio']={prev!r} is not one of the candidate ratios")
-    return best_mv, best_ratio
+    psnr = torch.stack([warp_psnr(ref, candidate_flow(model, x, ref, r), x) for r in ratios]).float().cpu()  # one sync
+    best, best_psnr = None, float("-inf")
+    for i in range(len(ratios)):
+        if psnr[i] > best_psnr:
+            best, best_psnr = i, psnr[i].item()
+    j = list(ratios).index(prev)
+    if best is None or ((best_psnr - psnr[j].item()) < bias and prev != ratios[best]):
+        best = j
+    return candidate_flow(model, x, ref, ratios[best]), ratios[best]

@@ -502,9 +502,10 @@ _GDN_IMPL = int(os.environ.get("B200VC_GDN_IMPL", "0"))  # 0 auto (tcgen05 when 
 _GDN_INPLACE_ADD = os.environ.get("B200VC_GDN_INPLACE_ADD", "1") != "0"
 
 
-def gdn(x, params, inverse=False, addend=None, impl=0):
+def gdn(x, params, inverse=False, addend=None, impl=0, inplace=None):
     """out = x * rsqrt(beta + gamma @ x^2) (IGDN: sqrt) [+ addend]; x is NCHW.  With ``addend`` the sum is
-    written into the addend's own storage (it is consumed) and that tensor is returned.
+    written into the addend's own storage (it is consumed) and that tensor is returned, unless ``inplace=False``
+    (a fresh output tensor; required when the addend must survive, e.g. when it is the block's own input).
     impl 0 = auto: the tcgen05 3xTF32 kernel for C == 128 (~1e-6 relative), else the exact-fp32 CUDA-core
     kernel; B200VC_GDN_IMPL=1 forces the exact kernel everywhere (bit-parity experiments)."""
     if impl == 0:
@@ -517,7 +518,9 @@ def gdn(x, params, inverse=False, addend=None, impl=0):
             raise RuntimeError("gdn: addend shape mismatch")
     # residual form: accumulate into the addend's storage (the reference's `out += identity`); the tcgen05
     # kernel then needs no addend traffic inside the SM -- the result tile leaves through a TMA reduce-add
-    out = addend if (addend is not None and _GDN_INPLACE_ADD) else torch.empty_like(x)
+    if inplace is None:
+        inplace = _GDN_INPLACE_ADD
+    out = addend if (addend is not None and inplace) else torch.empty_like(x)
     if x.numel() == 0:
         return out
     lib = _lib.load()

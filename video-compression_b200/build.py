@@ -19,7 +19,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
-]
+] + os.environ.get("NVCC_FLAGS", "").split()   # e.g. NVCC_FLAGS=-DB200VC_ENABLE_GDN_TRACE for tools/gdn_trace.py
 
 
 def _sources():

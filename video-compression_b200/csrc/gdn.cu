@@ -10,6 +10,8 @@
 // This file holds
 //   * gdn_prepare: NonNegativeParametrizer applied once per weight version (+ transposed / tf32-split images)
 //   * the CUDA-core fp32 kernel (exact fp32 FFMA; any C in {64,128,192}); the tcgen05 kernel is in gdn_tc.cu.
+#include <atomic>
+
 #include "common.cuh"
 
 namespace b200vc {
@@ -172,7 +174,7 @@ template <int C, int TP>
 static int launch_gdn_fp32(const float* x, const float* params, const float* addend, float* out, int N, int64_t HW,
                            int inverse, cudaStream_t st) {
   const size_t smem = (size_t)(C * C + C * TP) * sizeof(float);
-  static bool configured[64] = {false};
+  static std::atomic<bool> configured[64];  // zero-initialised; idempotent set-up, safe under concurrent hosts
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !configured[dev]) {

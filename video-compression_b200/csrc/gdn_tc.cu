@@ -24,6 +24,8 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "common.cuh"
 #include "gdn_tc_common.cuh"
 
@@ -418,23 +420,30 @@ static bool make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t 
   return r == CUDA_SUCCESS;
 }
 
-long long* g_trace = nullptr;  // set through b200vc_debug_set_gdn_trace (diagnostics only)
+#ifdef B200VC_ENABLE_GDN_TRACE
+long long* g_trace = nullptr;  // set through b200vc_debug_set_gdn_trace (debug builds only: include/b200vc_debug.h)
+#else
+static long long* const g_trace = nullptr;  // production builds carry no mutable global: the trace stores are dead code
+#endif
 
 template <class CFG, int INV>
 static int launch_inv(const CUtensorMap& map_x, const CUtensorMap& map_out, const CUtensorMap& map_add,
                       const float* params, const float* addend, int64_t HW, int tps, int total, int accumulate,
                       int grid, cudaStream_t st) {
-  static bool configured[64] = {false};
+  // once per device and instantiation, safe under concurrent host threads
+  static std::once_flag once[64];
+  static bool ok[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev >= 0 && dev < 64 && !configured[dev]) {
-    if (cudaFuncSetAttribute(gdn_tc_kernel<CFG, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             CFG::kSmemBytes) != cudaSuccess) {
-      set_error("gdn_f32: cannot reserve %d B of shared memory", CFG::kSmemBytes);
-      (void)cudaGetLastError();
-      return B200VC_EUNSUPPORTED;
-    }
-    configured[dev] = true;
+  if (dev < 0 || dev >= 64) return B200VC_EUNSUPPORTED;
+  std::call_once(once[dev], [&]() {
+    ok[dev] = cudaFuncSetAttribute(gdn_tc_kernel<CFG, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   CFG::kSmemBytes) == cudaSuccess;
+    if (!ok[dev]) (void)cudaGetLastError();
+  });
+  if (!ok[dev]) {
+    set_error("gdn_f32: cannot reserve %d B of shared memory", CFG::kSmemBytes);
+    return B200VC_EUNSUPPORTED;
   }
   gdn_tc_kernel<CFG, INV><<<grid, kThreads, CFG::kSmemBytes, st>>>(map_x, map_out, map_add, params, addend, HW, tps,
                                                                    total, accumulate, g_trace);
@@ -495,6 +504,11 @@ int launch_gdn_tc(const float* x, const float* params, const float* addend, floa
 
 }  // namespace b200vc
 
-// Diagnostics: device buffer of 256 x 16 clock64() stamps written by CTA 0 of the next tcgen05 GDN launches
-// (slots: 0 load issued, 1 raw landed, 2 split starts, 3 MMA issue, 4 epilogue starts, 5 store issued, 6 slot released).
-extern "C" void b200vc_debug_set_gdn_trace(long long* device_buffer) { b200vc::tc::g_trace = device_buffer; }
+#ifdef B200VC_ENABLE_GDN_TRACE
+// Diagnostics (debug builds: NVCC_FLAGS=-DB200VC_ENABLE_GDN_TRACE, include/b200vc_debug.h): device buffer of 256 x 16
+// clock64() stamps written by CTA 0 of the next tcgen05 GDN launches (slots: 0 load issued, 1 raw landed, 2 split
+// starts, 3 MMA issue, 4 epilogue starts, 5 store issued, 6 slot released).  The buffer must outlive every launch.
+extern "C" __attribute__((visibility("default"))) void b200vc_debug_set_gdn_trace(long long* device_buffer) {
+  b200vc::tc::g_trace = device_buffer;
+}
+#endif

@@ -13,6 +13,8 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "common.cuh"
 #include "warp_common.cuh"
 
@@ -451,7 +453,7 @@ int launch_warp_tma(const float* img, int64_t img_bs, const float* flow, const f
           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return B200VC_EUNSUPPORTED;
-  static bool configured[64][3] = {{false}};
+  static std::atomic<bool> configured[64][3];  // zero-initialised; idempotent set-up, safe under concurrent hosts
   int dev = 0;
   cudaGetDevice(&dev);
   dim3 grid((W + kTW - 1) / kTW, (H + kTH - 1) / kTH, N);
@@ -497,7 +499,7 @@ int launch_spynet_level_tma(const float* first, int64_t first_bs, const float* s
     return B200VC_EUNSUPPORTED;
   CUtensorMap map;
   if (!make_img_map(&map, second, N, H, W)) return B200VC_EUNSUPPORTED;
-  static bool configured[64] = {false};
+  static std::atomic<bool> configured[64];  // zero-initialised; idempotent set-up, safe under concurrent hosts
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !configured[dev]) {
@@ -532,7 +534,7 @@ int launch_warp2_tma(const float* xb, const float* xa, const float* flow_hat, co
     return B200VC_EUNSUPPORTED;
   CUtensorMap map_b, map_a;
   if (!make_img_map(&map_b, xb, N, H, W) || !make_img_map(&map_a, xa, N, H, W)) return B200VC_EUNSUPPORTED;
-  static bool configured[64] = {false};
+  static std::atomic<bool> configured[64];  // zero-initialised; idempotent set-up, safe under concurrent hosts
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !configured[dev]) {
