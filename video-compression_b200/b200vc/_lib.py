@@ -9,7 +9,7 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200vc.so")
+LIB_PATH = os.environ.get("B200VC_LIB") or os.path.join(_HERE, "libb200vc.so")   # B200VC_LIB: A/B timing of two builds
 
 WARP_LHBDC, WARP_FLEX, WARP_AC1 = 0, 1, 2
 ARITH_NO_FMA, ARITH_TRUE_DIV = 1, 2

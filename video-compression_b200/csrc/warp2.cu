@@ -179,7 +179,7 @@ warp2_kernel(const float* __restrict__ xb, const float* __restrict__ xa, const f
       for (int c = 0; c < 3; ++c)
         any |= __float_as_int(t[dir][c][0]) | __float_as_int(t[dir][c][1]) | __float_as_int(t[dir][c][2]) |
                __float_as_int(t[dir][c][3]);
-    const float zero = __int_as_float(any & g.arith);
+    const float zero = __int_as_float(any & g.zero);
 #pragma unroll
     for (int dir = 0; dir < 2; ++dir) {
 #pragma unroll
@@ -553,7 +553,7 @@ warp2_flex_kernel(const float* __restrict__ x0p, const float* __restrict__ x1p, 
       for (int c = 0; c < 3; ++c)
         any |= __float_as_int(v[dir][c][0]) | __float_as_int(v[dir][c][1]) | __float_as_int(v[dir][c][2]) |
                __float_as_int(v[dir][c][3]);
-    const float zero = __int_as_float(any & g.arith);
+    const float zero = __int_as_float(any & g.zero);
 #pragma unroll
     for (int c = 0; c < 4; ++c) __stcg(po + c * HW + o, f[c]);
 #pragma unroll

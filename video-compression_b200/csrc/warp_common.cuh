@@ -10,6 +10,7 @@ struct WarpGeom {
   float inv_x, inv_y;  // float(1.0 / ((W-1)/2))  (ATen CUDA: tensor / python scalar == tensor * float(1/scalar))
   float den_x, den_y;  // float((W-1)/2)         (ARITH_TRUE_DIV form)
   int variant, arith;
+  int zero;            // always 0, but only known at run time: the operand of the gather fence (warp2.cu)
 };
 
 // Reference arithmetic of the flow normalisation (see coords()): the divisor is the python float (W-1)/2 cast to fp32.
@@ -19,6 +20,7 @@ inline WarpGeom make_geom(int H, int W, int variant, int arith) {
   g.W = W;
   g.variant = variant;
   g.arith = arith;
+  g.zero = 0;
   const double dx = variant == B200VC_WARP_FLEX ? (double)W : ((double)W - 1.0) / 2.0;
   const double dy = variant == B200VC_WARP_FLEX ? (double)H : ((double)H - 1.0) / 2.0;
   g.den_x = (float)dx;
