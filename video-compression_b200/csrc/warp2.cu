@@ -267,18 +267,24 @@ warp2_staged_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_cons
   }
   const int qx0 = max((bx >> 2) - 1, 0), qy0 = max((by >> 2) - 1, 0);
   {
+    // 32-bit offsets from per-sample bases (a quarter-resolution plane set is far below 2^31 elements); the entry
+    // index is split with constant divisions once per entry, not per address
     const int q = h4 * w4;
+    const float* hat0 = flow_hat + (int64_t)n * 4 * q;
+    const float* ab0 = flow_ab + (int64_t)n * 2 * q;
+    const float* ba0 = flow_ba + (int64_t)n * 2 * q;
     for (int e = tid; e < 4 * kQR * kQC; e += kThreads) {
-      const int ch = e / (kQR * kQC), r = (e / kQC) % kQR, c = e % kQC;
+      const int ch = e / (kQR * kQC), rem = e - ch * (kQR * kQC), r = rem / kQC, c = rem - r * kQC;
       const int y0 = min(qy0 + r, hh - 1) * w4, y1 = min(qy0 + r + 1, hh - 1) * w4;
       const int x0 = min(qx0 + c, ww - 1), x1 = min(qx0 + c + 1, ww - 1);
-      const float* pri = (ch < 2 ? flow_ab : flow_ba) + ((int64_t)n * 2 + (ch & 1)) * q;
-      const float* hat = flow_hat + ((int64_t)n * 4 + ch) * q;
+      const float* pri = (ch < 2 ? ab0 : ba0) + (ch & 1) * q;
+      const float* hat = hat0 + ch * q;
+      const int o00 = y0 + x0, o01 = y0 + x1, o10 = y1 + x0, o11 = y1 + x1;
       float4 v;
-      v.x = __fadd_rn(__ldg(hat + y0 + x0), __ldg(pri + y0 + x0));
-      v.y = __fadd_rn(__ldg(hat + y0 + x1), __ldg(pri + y0 + x1));
-      v.z = __fadd_rn(__ldg(hat + y1 + x0), __ldg(pri + y1 + x0));
-      v.w = __fadd_rn(__ldg(hat + y1 + x1), __ldg(pri + y1 + x1));
+      v.x = __fadd_rn(__ldg(hat + o00), __ldg(pri + o00));
+      v.y = __fadd_rn(__ldg(hat + o01), __ldg(pri + o01));
+      v.z = __fadd_rn(__ldg(hat + o10), __ldg(pri + o10));
+      v.w = __fadd_rn(__ldg(hat + o11), __ldg(pri + o11));
       s_c[ch][r][c] = v;
     }
   }
@@ -299,19 +305,28 @@ warp2_staged_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_cons
 #pragma unroll 1
   for (int dir = 0; dir < 2; ++dir) {
     float ix[kPX], iy[kPX];
-    int mnx = 0x7fffffff, mxx = -0x7fffffff - 1, mny = 0x7fffffff, mxy = -0x7fffffff - 1;
+    float fmnx = 3.0e38f, fmxx = -3.0e38f, fmny = 3.0e38f, fmxy = -3.0e38f;
+    // The thread's 8 pixels sit in one column, 4 rows apart: consecutive upsample cells.  The x-interpolated lower
+    // edge of cell k IS the upper edge of cell k+1 (same inputs, same fma) -- computed once and carried along.
+    float topu = 0.f, topv = 0.f;
+    int prev_cell = -2;
 #pragma unroll
     for (int k = 0; k < kPX; ++k) {
       const int yr = by + ty + 4 * k;
       const int y = min(yr, g.H - 1);
       const float l0y = k == 0 ? cy0.l0 : cy1.l0, l1y = k == 0 ? cy0.l1 : cy1.l1;
       // rows past the frame (partial bottom tile) repeat the last row's cell; their results are never stored
-      const int ry = min((k == 0 ? cy0.i0 : cy1.i0 + (k - 1)), hh - 1) - qy0;
-      const float4 cu = s_c[2 * dir][min(ry, kQR - 1)][rc], cv = s_c[2 * dir + 1][min(ry, kQR - 1)][rc];
-      const float u = __fmaf_rn(l0y, __fmaf_rn(cx.l0, cu.x, __fmul_rn(cx.l1, cu.y)),
-                                __fmul_rn(l1y, __fmaf_rn(cx.l0, cu.z, __fmul_rn(cx.l1, cu.w))));
-      const float v = __fmaf_rn(l0y, __fmaf_rn(cx.l0, cv.x, __fmul_rn(cx.l1, cv.y)),
-                                __fmul_rn(l1y, __fmaf_rn(cx.l0, cv.z, __fmul_rn(cx.l1, cv.w))));
+      const int ry = min(min((k == 0 ? cy0.i0 : cy1.i0 + (k - 1)), hh - 1) - qy0, kQR - 1);
+      const float4 cu = s_c[2 * dir][ry][rc], cv = s_c[2 * dir + 1][ry][rc];
+      if (ry != prev_cell + 1) {   // first pixel, top-border clamp or bottom clamp: no edge to reuse
+        topu = __fmaf_rn(cx.l0, cu.x, __fmul_rn(cx.l1, cu.y));
+        topv = __fmaf_rn(cx.l0, cv.x, __fmul_rn(cx.l1, cv.y));
+      }
+      const float botu = __fmaf_rn(cx.l0, cu.z, __fmul_rn(cx.l1, cu.w));
+      const float botv = __fmaf_rn(cx.l0, cv.z, __fmul_rn(cx.l1, cv.w));
+      const float u = __fmaf_rn(l0y, topu, __fmul_rn(l1y, botu));
+      const float v = __fmaf_rn(l0y, topv, __fmul_rn(l1y, botv));
+      topu = botu; topv = botv; prev_cell = ry;
       if (FLOWS && xin && yr < g.H) {
         float* fo = flows_out + ((int64_t)n * 4 + dir * 2) * HW + o0 + 4 * k * g.W;
         __stcg(fo, u);
@@ -323,10 +338,12 @@ warp2_staged_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_cons
       const float py = __fmul_rn(__fmaf_rn(__fadd_rn(gy, 1.f), fH, -1.f), 0.5f);
       ix[k] = fminf(wmax, fmaxf(px, 0.f));
       iy[k] = fminf(hmax, fmaxf(py, 0.f));
-      const int x0 = (int)ix[k], y0 = (int)iy[k];      // >= 0 after the clip: truncation == floor
-      mnx = min(mnx, x0); mxx = max(mxx, x0);
-      mny = min(mny, y0); mxy = max(mxy, y0);
+      fmnx = fminf(fmnx, ix[k]); fmxx = fmaxf(fmxx, ix[k]);
+      fmny = fminf(fmny, iy[k]); fmxy = fmaxf(fmxy, iy[k]);
     }
+    // coordinates are >= 0 after the clip: truncation == floor, and floor is monotonic, so the box of the floors is
+    // the floor of the box
+    int mnx = (int)fmnx, mxx = (int)fmxx, mny = (int)fmny, mxy = (int)fmxy;
     // ---- block-wide bounding box of the footprint (taps x0..x0+1, y0..y0+1)
     mnx = __reduce_min_sync(0xffffffffu, mnx); mxx = __reduce_max_sync(0xffffffffu, mxx);
     mny = __reduce_min_sync(0xffffffffu, mny); mxy = __reduce_max_sync(0xffffffffu, mxy);
