@@ -223,8 +223,10 @@ B200VC_API int b200vc_gdn_f32(const float* x, const float* params, const float* 
  *   inv_gain (nullable) [C]: y_hat is multiplied per channel on the way out (Flex inv_gain_unit, layers.py:146);
  *   y_hat, lik (nullable) [N,C,HW]; symbols, indexes (nullable int32) [N,C,HW];
  *   scale_table [n_table] (needed iff indexes != NULL);
- *   bits_partials (nullable) double[N * blocks_per_sample]: per-CTA sums of -log2(lik); the grid is
- *   blocks_per_sample x N (use b200vc_reduce_blocks(C*HW)).
+ *   bits_partials (nullable) double[N * blocks_per_sample]: partial sums of -log2(lik).  Slot (n, b) covers a
+ *   contiguous 1/blocks_per_sample of sample n (whole 1024-element chunks); its value depends on those elements
+ *   only, never on the launch geometry (r2: a persistent grid walks the slots).  Any blocks_per_sample >= 1 works;
+ *   b200vc_reduce_blocks(C*HW / 4) (4096 elements per slot) is what the Python wrapper passes.
  *   Fused finish (every kernel that writes per-CTA partials has this pair): totals (nullable) double[N] + counters
  *   int32[N], counters ZERO on entry.  The CTA that finishes last for a sample sums that sample's partials in the
  *   same fixed order as b200vc_sum_partials_f64 (bit-identical result, independent of scheduling), writes totals[n]

@@ -562,7 +562,9 @@ def gauss_cond(y, scales, means, scale_bound=0.11, lik_bound=1e-9, inv_gain=None
     if y.numel() == 0:
         return {"y_hat": y_hat, "lik": lik, "bits": torch.zeros(N, device=dev, dtype=torch.float64) if want_bits else None,
                 "symbols": sym, "indexes": idx}
-    nb = reduce_blocks(C * H * W)
+    # one partial slot per 4096 elements: the persistent kernel needs no slot-per-CTA parallelism, and four units
+    # per lane and slot amortise the slot's log2 and warp reduction
+    nb = reduce_blocks((C * H * W + 3) // 4)
     part = torch.empty(N * nb, device=dev, dtype=torch.float64) if want_bits else None
     p = lambda t: t.data_ptr() if t is not None else None
     lib = _lib.load()

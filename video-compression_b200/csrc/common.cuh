@@ -62,6 +62,29 @@ struct Finish {
   int32_t* counters;
 };
 
+// The finishing CTA of a sample: re-reads ALL its partials in the strided order + tree of sum_partials_kernel
+// (blend.cu), writes totals[sample] and re-arms the counter.  Called by every thread of the CTA.
+template <int kThreads>
+__device__ __forceinline__ void finish_sample(const double* __restrict__ sample_partials, int n_per, int sample,
+                                              Finish f) {
+  static_assert(kThreads == 256, "must mirror sum_partials_kernel's 256-thread reduction order");
+  __threadfence();
+  double v = 0.0;
+  for (int k = threadIdx.x; k < n_per; k += kThreads) v += __ldcg(sample_partials + k);
+  __shared__ double s_fin[kThreads / 32];
+  v = warp_sum(v);
+  __syncthreads();  // s_fin may still be read by a previous call
+  if ((threadIdx.x & 31) == 0) s_fin[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < kThreads / 32; ++i) t += s_fin[i];
+    f.totals[sample] = t;
+    f.counters[sample] = 0;
+  }
+}
+
 // Must be called by every thread of the CTA; `tot` is read from thread 0 only.
 template <int kThreads>
 __device__ __forceinline__ void publish_partial(double tot, double* __restrict__ sample_partials, int idx,
@@ -80,20 +103,7 @@ __device__ __forceinline__ void publish_partial(double tot, double* __restrict__
   if (f.totals == nullptr) return;  // uniform
   __syncthreads();
   if (!s_last) return;
-  __threadfence();
-  double v = 0.0;
-  for (int k = threadIdx.x; k < n_per; k += kThreads) v += __ldcg(sample_partials + k);
-  __shared__ double s_fin[kThreads / 32];
-  v = warp_sum(v);
-  if ((threadIdx.x & 31) == 0) s_fin[threadIdx.x >> 5] = v;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double t = 0.0;
-#pragma unroll
-    for (int i = 0; i < kThreads / 32; ++i) t += s_fin[i];
-    f.totals[sample] = t;
-    f.counters[sample] = 0;
-  }
+  finish_sample<kThreads>(sample_partials, n_per, sample, f);
 }
 
 // ATen CUDA sigmoid for float: 1 / (1 + exp(-x)).
@@ -117,5 +127,18 @@ __device__ __forceinline__ void st_stream4(int32_t* p, const int4& v) {
                "r"(v.z), "r"(v.w)
                : "memory");
 }
+
+// Ampere-style asynchronous copies global -> shared (LDGSTS), L2-only caching for 16-byte copies.
+template <int kBytes>
+__device__ __forceinline__ void cp_async(uint32_t smem_dst, const void* gmem_src) {
+  static_assert(kBytes == 4 || kBytes == 16, "cp.async size");
+  if constexpr (kBytes == 16)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
 
 }  // namespace b200vc
