@@ -9,8 +9,8 @@ from b200vc import ops
 g = torch.Generator().manual_seed(0)
 H, W = 1088, 1920
 flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda")
-tag = os.environ.get("B200VC_WARP2_TMA", "0")
-for N in (1, 4):
+tag = "pipe=" + os.environ.get("B200VC_WARP2_PIPE", "1") + " tma=" + os.environ.get("B200VC_WARP2_TMA", "0")
+for N in [int(a) for a in sys.argv[1:]] or (1, 4, 16):
     xb = torch.rand(N, 3, H, W, generator=g).cuda()
     xa = torch.rand(N, 3, H, W, generator=g).cuda()
     sm = lambda c, a: torch.nn.functional.interpolate(a * torch.randn(N, c, 20, 32, generator=g), size=(272, 480), mode="bilinear").cuda()
@@ -27,4 +27,4 @@ for N in (1, 4):
             tot += s.elapsed_time(e)
         ms = tot / 8
         gb = 50 * N * H * W / ms / 1e6
-        print(f"WARP2_TMA={tag} N={N} {kind:6s}: {ms*1e3:7.1f} us {gb:5.0f} GB/s ({gb/6539.2:.1%})", flush=True)
+        print(f"{tag} N={N} {kind:6s}: {ms*1e3:7.1f} us {gb:5.0f} GB/s ({gb/6539.2:.1%})", flush=True)
