@@ -6,11 +6,6 @@ import re
 import sys
 from collections import defaultdict
 
-MINE = ("gdn_tc_kernel", "gdn_fp32_kernel", "gdn_prepare_kernel", "warp_tma_kernel", "warp2_tma_kernel", "warp_kernel",
-        "warp2_lhbdc_kernel", "warp2_half_sse_kernel", "warp_sse_kernel", "blend_kernel", "sse_u8_kernel",
-        "sum_partials_kernel", "gauss_cond_kernel", "eb_prepare_kernel", "entropy_bottleneck_kernel",
-        "spynet_level_kernel", "spynet_pyramid_kernel", "rans_", "deform_conv2d", "dcn_to_group_last_kernel",
-        "round_checker_kernel", "checker_mask_kernel")
 rows = []
 with open(sys.argv[1]) as f:
     lines = [ln for ln in f if ln.startswith('"')]
@@ -26,9 +21,10 @@ for r in csv.DictReader(lines):
 
 def family(name):
     name = re.sub(r"^void ", "", name)
-    m = re.match(r"((?:b200vc::)?(?:tc::|wt::)?(?:%s))" % "|".join(MINE), name)
-    if m:
-        return "b200vc::" + m.group(1).replace("b200vc::", "")
+    base = re.split(r"[<(]", name)[0]
+    # every kernel of the library lives in namespace b200vc (ncu drops the outer namespace of nested ones: tc::, wt::, w3::)
+    if base.startswith("b200vc::") or re.match(r"(tc|tc192|wt|w2|w3|wf)::", base):
+        return "b200vc::" + base.replace("b200vc::", "")
     m = re.match(r"((?:at::native::|at::|cudnn::|cutlass::)?[\w:]*?\w+)[<(]", name)
     base = m.group(1) if m else name.split("(")[0]
     if base.startswith("at::"):
