@@ -158,3 +158,71 @@ def test_bit_sums_are_deterministic_and_shape_only():
     y2, s2, m2 = (torch.cat([t, t.flip(0)], 0) for t in (y, sigma, mu))
     c = ops.gauss_cond(y2, s2, m2, want_y_hat=False, want_lik=False)["bits"]
     assert c[0].item() == a[0].item() and c[1].item() == a[0].item()
+
+
+# ---- round 2: persistent K-GC (partial slots walked by resident CTAs, per-thread cp.async ring, packed fp32) ----------
+@pytest.mark.parametrize("shape", [(1, 1, 1, 4), (3, 1, 1, 3), (2, 7, 5, 9), (2, 8, 16, 8), (5, 3, 33, 31), (1, 16, 17, 60),
+                                   (300, 2, 2, 2), (2, 128, 20, 32), (1, 5, 205, 4), (3, 1, 64, 64), (1, 1, 64, 65),
+                                   (2, 12, 34, 60)])
+def test_gauss_cond_slot_geometry_edge_shapes(shape):
+    """Vector (HW % 4 == 0) and scalar path, one slot per sample, hundreds of samples per CTA, partial last chunks, sizes
+    around the 1024-element chunk and 4096-element slot boundaries; one element at the scale bound, one in erfc's far
+    tail (the guarded form).  Every output is bit-equal to the oracle chain; both kernel forms give the same totals."""
+    from b200vc import ops
+    o, _ = _gc()
+    N, C, H, W = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    r = lambda: torch.randn(N, C, H, W, generator=g).cuda()
+    y, s, m = 4 * r(), r().abs() * 3, r()
+    s[0, 0, 0, 0] = 0.0
+    y.view(-1)[-1] = 60.0
+    table = o.scale_table
+    out = ops.gauss_cond(y, s, m, want_lik=True, want_bits=True, want_symbols=True, scale_table=table)
+    lean = ops.gauss_cond(y, s, m, want_lik=False, want_bits=True)
+    with torch.no_grad():
+        yh, lik = o(y, s, means=m)
+    assert torch.equal(out["y_hat"], yh) and torch.equal(lean["y_hat"], yh)
+    assert torch.equal(out["lik"], lik)
+    assert torch.equal(out["symbols"], torch.round(yh - m).int())
+    assert torch.equal(out["indexes"], o.build_indexes(s))
+    ref = -torch.log2(lik.double()).flatten(1).sum(1)
+    for res in (out, lean):
+        assert ((res["bits"] - ref).abs() <= 1e-6 * ref.abs() + 1e-6).all()
+
+
+def test_gauss_cond_operands_near_the_exponent_limits_take_the_scalar_routines():
+    """sigma or |y - mu| beyond 2^59 leave the shared-reciprocal division's proven range: the kernel must fall back to
+    __fdiv_rn / erfcf element by element and still equal the oracle bit for bit."""
+    from b200vc import ops
+    o, _ = _gc()
+    g = torch.Generator().manual_seed(11)
+    y = (3 * torch.randn(1, 4, 8, 16, generator=g)).cuda()
+    s = (torch.rand(1, 4, 8, 16, generator=g) * 2).cuda()
+    m = torch.randn(1, 4, 8, 16, generator=g).cuda()
+    s[0, 1, 2, 3] = 3.0e19          # > 2^59
+    y[0, 2, 5, 7] = -2.5e30
+    s[0, 3, 0, 0] = float("inf")
+    with torch.no_grad():
+        yh, lik = o(y, s, means=m)
+    out = ops.gauss_cond(y, s, m, want_lik=True, want_bits=True)
+    assert torch.equal(out["y_hat"], yh)
+    assert torch.equal(out["lik"], lik)
+
+
+def test_packed_fp32_likelihood_arithmetic_is_bit_identical_to_libdevice():
+    """tools/gc_math_check: erfc2 (csrc/gc_math.cuh) against erfcf over ALL 2^32 arguments in every template form, the
+    shared-reciprocal division against __fdiv_rn over 2e10 in-range quotients.  0 mismatches, exit code 0."""
+    import json
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tools", "_bin", "gc_math_check")
+    if not os.path.exists(exe):
+        os.makedirs(os.path.dirname(exe), exist_ok=True)
+        subprocess.run(["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-o", exe,
+                        os.path.join(root, "tools", "gc_math_check.cu")], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    rep = json.loads(r.stdout.strip().splitlines()[-1])
+    print(rep)
+    assert r.returncode == 0
+    assert rep["erfc2_mismatch"] == 0 and rep["div2_mismatch_random"] == 0 and rep["div2_mismatch_gc_shaped"] == 0
