@@ -1019,7 +1019,7 @@ def run_product(args):
         phase("e2e region done")
         tf32_ms = None
         tf32_steps = min(steps, 2)
-        if not (args.conv_tf32 or args.no_tf32_leg or whole_sequence or args.ncu_range):
+        if not (args.conv_tf32 or args.no_tf32_leg or whole_sequence or args.ncu_range or world > 1):   # 1-GPU runs only
             torch.backends.cudnn.allow_tf32 = True
             wl.step(0, False)
             bd.barrier()
