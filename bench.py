@@ -62,6 +62,10 @@ def parse():
                     help="let cuDNN use TF32 for the (out-of-scope) convolutions, as torch defaults do")
     ap.add_argument("--cudnn-benchmark-limit", type=int, default=None,
                     help="torch.backends.cudnn.benchmark_limit: engine configs the autotuner tries per convolution shape")
+    ap.add_argument("--code-anchors", type=int, default=0, metavar="Q",
+                    help="lhbdc_gop8: code both anchors of every GOP with an mbt2018_mean(Q)-shaped I-frame codec "
+                         "(random-init; LHBDC/test/testing.py:78-86,209) instead of using the source frames; the "
+                         "metric still counts B-frames only")
     ap.add_argument("--no-tf32-leg", action="store_true",
                     help="skip the extra labelled timing with cuDNN TF32 convolutions (torch's default precision)")
     ap.add_argument("--deterministic", action="store_true",
@@ -280,7 +284,13 @@ class LhbdcGop8(Workload):
         self.device, self.rank, self.world = device, rank, world
         self.sched = gop.LHBDC_GOP8
         self.model = build_lhbdc(device)
-        self.coder = gop.GopCoder(self.model, self.sched)
+        self.anchor_codec = None
+        if self.args.code_anchors:
+            from b200vc import modules
+            torch.manual_seed(100 + self.args.code_anchors)
+            self.anchor_codec = modules.mbt2018_mean(self.args.code_anchors).eval().to(device)
+            self.anchor_codec.update(force=True)
+        self.coder = gop.GopCoder(self.model, self.sched, anchor_codec=self.anchor_codec)
         g, h, w, G = self.sched.gop, self.h, self.w, self.G
         if self.T:
             # one shared sequence; this rank holds the frames of its contiguous block of GOPs (anchors duplicated
@@ -378,7 +388,9 @@ class LhbdcGop8(Workload):
                      f"{self.G} GOP-8 per GPU = {self.G * len(self.sched.refs)} B-frames, levels batched "
                      f"({self.G}/{2 * self.G}/{4 * self.G} frames per call)"),
             "weights": "random-init (seed 0) + deterministic calibration (b200vc/synthetic.py)",
-            "anchors": "uncoded source frames (I-frame codec is outside the B-frame hot path)",
+            "anchors": (f"both anchors of every GOP coded by an mbt2018_mean(q={self.args.code_anchors})-shaped I-frame "
+                        "codec (random-init), not counted in the metric" if self.args.code_anchors else
+                        "uncoded source frames (I-frame codec is outside the B-frame hot path)"),
             "conv_math": _conv_math(self.args),
             "l2": "inputs larger than L2: each step streams >= 224 MB of frames + GBs of activations; "
                   "two GOP sets alternate",

@@ -170,3 +170,63 @@ def test_forward_device_is_cuda_graph_capturable(models, triple):
         want_x, want_bits, _ = prod.forward_device(xa, xc, xb)
     assert torch.equal(got_bits, want_bits)
     assert torch.equal(got_x, want_x)
+
+
+# ---- I-frame anchors: mbt2018_mean-shaped codec (LHBDC/test/testing.py:78-86,209) ----------------------------------
+@pytest.mark.parametrize("quality", [3, 7])
+def test_mbt2018_mean_anchor_codec_matches_oracle(strict_fp32, quality):
+    """The product mirror (GDN C = 128 / 192 on tcgen05, K-EB, K-GC) vs the oracle's CompressAI-shaped
+    MeanScaleHyperprior with the same random-init weights: image_compress (decoded image, bits)."""
+    from b200vc import modules as M
+    from b200vc import synthetic
+    from oracle import cai
+    torch.manual_seed(quality)
+    N, Mm = M.MBT2018_MEAN_CFG[quality]
+    orc = cai.MeanScaleHyperprior(N, Mm).eval()
+    orc.keep_latents = True
+    prod = M.mbt2018_mean(quality).eval()
+    prod.load_state_dict(orc.state_dict())
+    orc.update(force=True); prod.update(force=True)
+    orc.cuda(); prod.cuda()
+    x = synthetic.make_sequence(2, 128, 192, seed=3, device="cuda")
+    with torch.no_grad():
+        out = orc(x)
+        want_bits = sum((torch.log(l.double()).flatten(1).sum(1) / -np.log(2.0)) for l in out["likelihoods"].values())
+        x_hat, bits = M.image_compress(x, prod)
+        api = prod(x)                                   # CompressAI-style result dict through the same kernels
+    rel = ((bits - want_bits).abs() / want_bits).max().item()
+    dx = (x_hat - out["x_hat"]).abs().max().item()
+    sym_o = torch.round(out["latents"]["y_hat"] - out["latents"]["means_hat"])
+    _, _, _, parts = prod.forward_bits(x, want_symbols=True)
+    same = (parts["y_symbols"].float() == sym_o).float().mean().item()
+    print(f"mbt2018_mean q={quality} (N={N}, M={Mm}): bits rel {rel:.2e}, x_hat max|d| {dx:.2e}, y symbols equal {same:.6f}")
+    assert rel < 1e-4 and same > 0.9999
+    assert dx < 1e-3 * max(1.0, out["x_hat"].abs().max().item())
+    assert torch.allclose(api["x_hat"], x_hat) and set(api["likelihoods"]) == {"y", "z"}
+
+
+def test_gop_coder_codes_anchors_with_an_i_frame_codec(models):
+    """GopCoder(anchor_codec=...): anchors go through image_compress first (testing.py:127-152), B-frames are predicted
+    from the DECODED anchors, and the anchors' bits / SSE are booked."""
+    from b200vc import gop, synthetic
+    from b200vc import modules as M
+    _, prod = models
+    torch.manual_seed(1)
+    icodec = M.mbt2018_mean(3).eval().cuda()
+    icodec.update(force=True)
+    frames = synthetic.make_sequence(17, 192, 192, seed=5, device="cuda")
+    gops = torch.stack([frames[0:9], frames[8:17]], 0)
+    coder = gop.GopCoder(prod, gop.LHBDC_GOP8, anchor_codec=icodec)
+    bits, sse, dec = coder.code(gops, (180, 190), want_decoded=True)
+    with torch.no_grad():
+        d, s = M.image_compress(torch.cat([gops[:, 0], gops[:, 8]], 0), icodec)   # the coder's own batch composition
+        d0, d8, s0, s8 = d[:2], d[2:], s[:2], s[2:]
+        _, b4, _ = prod.forward_device(d0, gops[:, 4], d8)
+    # (cuDNN's transposed convolutions are not run-to-run deterministic: last-ulp differences in the decoded anchors)
+    assert torch.allclose(dec[:, 0], d0, rtol=1e-4, atol=1e-5) and torch.allclose(dec[:, 8], d8, rtol=1e-4, atol=1e-5)
+    assert ((bits[:, 0] - s0).abs() / s0 < 1e-6).all() and ((bits[:, 8] - s8).abs() / s8 < 1e-6).all()
+    assert (sse[:, [0, 8]] > 0).all() and (bits > 0).all()
+    assert ((bits[:, 4] - b4).abs() / b4 < 1e-4).all()
+    # the same GOPs without the codec: anchors uncoded, frame 4 predicted from the source frames
+    plain, _ = gop.GopCoder(prod, gop.LHBDC_GOP8).code(gops, (180, 190))
+    assert (plain[:, [0, 8]] == 0).all() and not torch.equal(plain[:, 4], bits[:, 4])

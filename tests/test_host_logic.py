@@ -209,3 +209,24 @@ def test_flowguided_mirror_has_the_reference_checkpoint_layout():
         assert flowguided.select_references(order, buf) == o_fg.select_references(order, buf)
     assert flowguided.get_scales(4, 0, 8) == o_fg.get_scales(4, 0, 8) == (0.5, 0.5)
     assert flowguided.get_scales(3, 3, 3) == (0, 0)
+
+
+def test_mbt2018_mean_mirror_has_compressai_topology_and_keys():
+    """b200vc.modules.mbt2018_mean(q): CompressAI's cfgs["mbt2018-mean"] widths, the oracle's (CompressAI-shaped)
+    state-dict keys, the zoo function's argument checks (LHBDC/test/testing.py:209)."""
+    import pytest
+    from b200vc import modules as M
+    from oracle import cai
+    assert M.MBT2018_MEAN_CFG[4] == (128, 192) and M.MBT2018_MEAN_CFG[5] == (192, 320) and len(M.MBT2018_MEAN_CFG) == 8
+    for q in (1, 7):
+        N, Mm = M.MBT2018_MEAN_CFG[q]
+        prod, orc = M.mbt2018_mean(q), cai.MeanScaleHyperprior(N, Mm)
+        assert sorted(prod.state_dict()) == sorted(orc.state_dict())
+        assert all(prod.state_dict()[k].shape == v.shape for k, v in orc.state_dict().items())
+        prod.load_state_dict(orc.state_dict(), strict=True)
+    with pytest.raises(ValueError):
+        M.mbt2018_mean(9)
+    with pytest.raises(ValueError):
+        M.mbt2018_mean(3, metric="ms-ssim")
+    with pytest.raises(RuntimeError):
+        M.mbt2018_mean(3, pretrained=True)

@@ -82,16 +82,21 @@ class GopCoder:
     193-200 passes ``n=[n], l=l`` per frame level), ``forward_device(x_before, x_current, x_after, [n], l)``
     (``BidirFlowRef``).
 
-    ``code(frames, crop)``: frames [G, gop+1, 3, H, W] (G independent GOPs, padded size), anchors are used
-    as-is (uncoded) -- I-frame coding is outside the B-frame hot path.  Returns device tensors
-    ``bits[G, gop+1]`` (0 for anchors) and ``sse[G, gop+1]`` (uint8-domain, over the unpadded crop) without
-    any host synchronisation.
+    ``code(frames, crop)``: frames [G, gop+1, 3, H, W] (G independent GOPs, padded size).  Without an
+    ``anchor_codec`` the anchors are used as-is (uncoded: I-frame coding is outside the B-frame hot path); with one
+    (``b200vc.modules.mbt2018_mean(q)`` or any module with ``forward_bits``) both anchors of every GOP go through
+    ``image_compress`` first, as the reference's evaluation loop does (LHBDC/test/testing.py:127-152: ``decoded[0]``,
+    ``decoded[8]`` are the I-codec's reconstructions and their sizes are booked as I-frames) -- a GOP's last anchor
+    is coded again as the next GOP's first one, which is what keeps the GOPs independent units.  Returns device tensors
+    ``bits[G, gop+1]`` (0 for uncoded anchors) and ``sse[G, gop+1]`` (uint8-domain, over the unpadded crop) without any
+    host synchronisation.
     """
 
-    def __init__(self, model, schedule=LHBDC_GOP8, level_quality=None):
+    def __init__(self, model, schedule=LHBDC_GOP8, level_quality=None, anchor_codec=None):
         self.model = model
         self.schedule = schedule
         self.level_quality = level_quality
+        self.anchor_codec = anchor_codec
 
     @torch.no_grad()
     def code(self, frames, crop, want_decoded=False):
@@ -104,6 +109,14 @@ class GopCoder:
         decoded = {0: frames[:, 0], sch.gop: frames[:, sch.gop]}
         bits = torch.zeros((G, T), device=dev, dtype=torch.float64)
         sse = torch.zeros((G, T), device=dev, dtype=torch.float64)
+        if self.anchor_codec is not None:
+            from .modules import image_compress
+            both = torch.cat([frames[:, 0], frames[:, sch.gop]], 0)       # first and last anchors of all GOPs: one call
+            dec, size = image_compress(both, self.anchor_codec)
+            a_sse = ops.sse_u8(dec, both, h, w)
+            decoded = {0: dec[:G], sch.gop: dec[G:]}
+            bits[:, 0], bits[:, sch.gop] = size[:G], size[G:]
+            sse[:, 0], sse[:, sch.gop] = a_sse[:G], a_sse[G:]
         for level, level_frames in enumerate(sch.by_level()):
             xb = torch.cat([decoded[sch.refs[f][0]] for f in level_frames], 0)
             xa = torch.cat([decoded[sch.refs[f][1]] for f in level_frames], 0)

@@ -469,6 +469,49 @@ def _deconv5(i, o, stride=2):
     return nn.ConvTranspose2d(i, o, kernel_size=5, stride=stride, output_padding=stride - 1, padding=2)
 
 
+# CompressAI's `mbt2018-mean` configurations (compressai/zoo/image.py: cfgs["mbt2018-mean"]): quality -> (N, M)
+MBT2018_MEAN_CFG = {1: (128, 192), 2: (128, 192), 3: (128, 192), 4: (128, 192),
+                    5: (192, 320), 6: (192, 320), 7: (192, 320), 8: (192, 320)}
+
+
+class Mbt2018Mean(MeanScaleHyperprior):
+    """``compressai.models.MeanScaleHyperprior`` with its own sub-networks -- the I-frame codec the reference's
+    evaluation loops build with ``mbt2018_mean(args.i_qual, "mse", pretrained=True)`` (LHBDC/test/testing.py:209,
+    Flex-Rate.../test/testing.py) and call through ``image_compress`` (testing.py:78-86).  Same member names and
+    state-dict keys as CompressAI's class, so ``compressai.zoo`` checkpoints load unchanged; GDN / IGDN (C = N: 128 or
+    192, both on the tcgen05 kernel), the factorised prior and the Gaussian conditional run on the b200vc kernels."""
+
+    def __init__(self, N=192, M=320):
+        super().__init__(N, M)
+        self.g_a = nn.Sequential(_conv5(3, N), GDN(N), _conv5(N, N), GDN(N), _conv5(N, N), GDN(N), _conv5(N, M))
+        self.g_s = nn.Sequential(_deconv5(M, N), GDN(N, inverse=True), _deconv5(N, N), GDN(N, inverse=True),
+                                 _deconv5(N, N), GDN(N, inverse=True), _deconv5(N, 3))
+        self.h_a = nn.Sequential(nn.Conv2d(M, N, 3, 1, 1), nn.LeakyReLU(inplace=True), _conv5(N, N),
+                                 nn.LeakyReLU(inplace=True), _conv5(N, N))
+        self.h_s = nn.Sequential(_deconv5(N, M), nn.LeakyReLU(inplace=True), _deconv5(M, M * 3 // 2),
+                                 nn.LeakyReLU(inplace=True), nn.Conv2d(M * 3 // 2, M * 2, 3, 1, 1))
+
+
+def mbt2018_mean(quality, metric="mse", pretrained=False):
+    """``compressai.zoo.mbt2018_mean`` without the download: the architecture for ``quality`` with fresh weights
+    (load a CompressAI checkpoint with ``load_state_dict``; there is no network access here for ``pretrained``)."""
+    if metric != "mse":
+        raise ValueError(f"mbt2018_mean: unknown metric {metric!r}")
+    if quality not in MBT2018_MEAN_CFG:
+        raise ValueError(f'Invalid quality "{quality}", should be between (1, 8)')
+    if pretrained:
+        raise RuntimeError("mbt2018_mean: pretrained weights cannot be downloaded here; build the model and "
+                           "load_state_dict() a compressai.zoo checkpoint")
+    return Mbt2018Mean(*MBT2018_MEAN_CFG[quality])
+
+
+def image_compress(im, compressor):
+    """LHBDC/test/testing.py:78-86 -- ``(decoded image, size in bits)`` of an I-frame codec; here the likelihood
+    tensors are never written (``forward_bits``), the size comes back as a float64 tensor [N] without a host sync."""
+    x_hat, bits_y, bits_z = compressor.forward_bits(im)
+    return x_hat, bits_y + bits_z
+
+
 class MaskedConv2d(nn.Conv2d):
     """compressai.layers.MaskedConv2d (causal PixelCNN mask).  Present in the ICIP checkpoints as
     ``context_prediction`` (created by the base class below), never called by those models."""
