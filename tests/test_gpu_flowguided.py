@@ -54,8 +54,10 @@ def test_elic_bottlenecks_match_oracle(models, which, s):
                 rel = ((got[k][name] - want[k][name]).abs() / want[k][name]).max().item()
                 assert rel < 1e-4, (name, rel)
         else:
+            # decoded tensors: cuDNN convolutions over differently laid-out inputs on the two sides; seen 1.2e-8 .. 1.15e-5
+            # relative depending on the box (a flipped symbol would show as >= 1e-2), bar 5e-5
             d = (got[k] - want[k]).abs().max().item()
-            assert d <= 1e-5 * max(1.0, want[k].abs().max().item()), (k, d)
+            assert d <= 5e-5 * max(1.0, want[k].abs().max().item()), (k, d)
     b_o = _bits64(want)
     rel = abs(got_b["bits"].sum().item() - b_o) / b_o
     print(f"{which} s={s}: bits oracle {b_o:.2f}, bits-only pass rel {rel:.2e}")
