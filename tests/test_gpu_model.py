@@ -202,7 +202,8 @@ def test_mbt2018_mean_anchor_codec_matches_oracle(strict_fp32, quality):
     print(f"mbt2018_mean q={quality} (N={N}, M={Mm}): bits rel {rel:.2e}, x_hat max|d| {dx:.2e}, y symbols equal {same:.6f}")
     assert rel < 1e-4 and same > 0.9999
     assert dx < 1e-3 * max(1.0, out["x_hat"].abs().max().item())
-    assert torch.allclose(api["x_hat"], x_hat) and set(api["likelihoods"]) == {"y", "z"}
+    # two passes through cuDNN's transposed convolutions (not run-to-run deterministic in the last ulp)
+    assert torch.allclose(api["x_hat"], x_hat, rtol=1e-4, atol=1e-5) and set(api["likelihoods"]) == {"y", "z"}
 
 
 def test_gop_coder_codes_anchors_with_an_i_frame_codec(models):
